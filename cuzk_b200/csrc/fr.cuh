@@ -1,0 +1,284 @@
+// fr.cuh -- BN254 scalar-field "reference arithmetic" on 8 x 32-bit limbs for sm_100a.
+//
+// Every function here evaluates, bit for bit, what the reference CPU code computes
+// (src/poseidon/field_arithmetic.cpp), including its non-modular corner semantics:
+//   add      :172-182   (a + b) mod 2^256, then reduce            -> fr_add_general / fr_add_canon
+//   subtract :184-219   conditional +p, limb-wise borrow quirk     -> fr_sub_ref
+//   reduce   :244-248   while (a >= p) a -= p  (quotient <= 5)     -> fr_reduce
+//   multiply :221-238 + reduce_512 :250-330                        -> fr_mul / fr_sqr / fr_pow5
+// The exact formulas are restated in DESIGN.md ("Arithmetic the kernels evaluate").
+//
+// Implementation: 32x32->64 multiply-adds issue as IMAD.WIDE.U32(.X) -- ptxas fuses each
+// mad.lo.cc / madc.hi.cc pair below into one IMAD.WIDE with predicate carry in/out.  Products
+// are accumulated in two interleaved sets of 64-bit lanes (even / odd 32-bit positions), so a
+// row of four products is one carry chain with no per-product carry fix-up.
+#pragma once
+#include <cstdint>
+
+namespace cuzk {
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+// p = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001  (field_arithmetic.cpp:12-14)
+#define CUZK_P0 0xf0000001u
+#define CUZK_P1 0x43e1f593u
+#define CUZK_P2 0x79b97091u
+#define CUZK_P3 0x2833e848u
+#define CUZK_P4 0x8181585du
+#define CUZK_P5 0xb85045b6u
+#define CUZK_P6 0xe131a029u
+#define CUZK_P7 0x30644e72u
+// k = 2^256 mod p = 0x0e0a77c19a07df2f666ea36f7879462e36fc76959f60cd29ac96341c4ffffffb  (:256-258)
+#define CUZK_K0 0x4ffffffbu
+#define CUZK_K1 0xac96341cu
+#define CUZK_K2 0x9f60cd29u
+#define CUZK_K3 0x36fc7695u
+#define CUZK_K4 0x7879462eu
+#define CUZK_K5 0x666ea36fu
+#define CUZK_K6 0x9a07df2fu
+#define CUZK_K7 0x0e0a77c1u
+
+struct Fr {
+  u32 v[8];
+};
+
+template <int I> struct PW;   // limbs of 1p
+template <> struct PW<0> { static constexpr u32 v = CUZK_P0; };
+template <> struct PW<1> { static constexpr u32 v = CUZK_P1; };
+template <> struct PW<2> { static constexpr u32 v = CUZK_P2; };
+template <> struct PW<3> { static constexpr u32 v = CUZK_P3; };
+template <> struct PW<4> { static constexpr u32 v = CUZK_P4; };
+template <> struct PW<5> { static constexpr u32 v = CUZK_P5; };
+template <> struct PW<6> { static constexpr u32 v = CUZK_P6; };
+template <> struct PW<7> { static constexpr u32 v = CUZK_P7; };
+
+// limb i of m*p for m in {1,2,4} (all < 2^256), evaluated at compile time
+__host__ __device__ constexpr u32 mulp_limb(int m, int i) {
+  const u32 p[8] = {CUZK_P0, CUZK_P1, CUZK_P2, CUZK_P3, CUZK_P4, CUZK_P5, CUZK_P6, CUZK_P7};
+  u64 carry = 0;
+  u32 out = 0;
+  for (int j = 0; j <= i; ++j) {
+    u64 t = (u64)p[j] * (u64)m + carry;
+    out = (u32)t;
+    carry = t >> 32;
+  }
+  return out;
+}
+
+__host__ __device__ constexpr u32 k_limb(int i) {
+  const u32 k[8] = {CUZK_K0, CUZK_K1, CUZK_K2, CUZK_K3, CUZK_K4, CUZK_K5, CUZK_K6, CUZK_K7};
+  return k[i];
+}
+
+// ---- single-instruction carry-chain primitives (CGBN style; volatile keeps PTX order) ----
+__device__ __forceinline__ u32 add_cc(u32 a, u32 b) { u32 r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ u32 addc_cc(u32 a, u32 b) { u32 r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ u32 addc(u32 a, u32 b) { u32 r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ u32 sub_cc(u32 a, u32 b) { u32 r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ u32 subc_cc(u32 a, u32 b) { u32 r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ u32 subc(u32 a, u32 b) { u32 r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ u32 mad_lo_cc(u32 a, u32 b, u32 c) { u32 r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ u32 madc_lo_cc(u32 a, u32 b, u32 c) { u32 r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ u32 madc_hi_cc(u32 a, u32 b, u32 c) { u32 r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ u32 madc_hi(u32 a, u32 b, u32 c) { u32 r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ u32 madc_lo(u32 a, u32 b, u32 c) { u32 r; asm volatile("madc.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ u32 mad_lo(u32 a, u32 b, u32 c) { return a * b + c; }
+
+// (hi:lo) = a*b + (hi:lo) as one IMAD.WIDE.U32 (no carry in/out)
+__device__ __forceinline__ void mad_wide(u32 &lo, u32 &hi, u32 a, u32 b) {
+  u64 t = (u64)a * (u64)b + (((u64)hi << 32) | lo);
+  lo = (u32)t;
+  hi = (u32)(t >> 32);
+}
+
+// ---- comparisons / conditional subtract ----
+// x -= m*p if x >= m*p   (m in {1,2,4}); 8 IADD3.X + 8 SEL
+template <int M>
+__device__ __forceinline__ void cond_sub_mp(u32 (&x)[8]) {
+  u32 d[8];
+  d[0] = sub_cc(x[0], mulp_limb(M, 0));
+#pragma unroll
+  for (int i = 1; i < 8; ++i) d[i] = subc_cc(x[i], mulp_limb(M, i));
+  u32 borrow = subc(0u, 0u);  // 0xffffffff when x < m*p
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = borrow ? x[i] : d[i];
+}
+
+// reduce : field_arithmetic.cpp:244-248.  Exact x mod p for ANY 256-bit x (quotient <= 5).
+__device__ __forceinline__ void fr_reduce(u32 (&x)[8]) {
+  cond_sub_mp<4>(x);
+  cond_sub_mp<2>(x);
+  cond_sub_mp<1>(x);
+}
+
+// add for canonical operands (a, b < p): sum < 2p < 2^256, at most one subtraction.
+__device__ __forceinline__ void fr_add_canon(u32 (&r)[8], const u32 (&a)[8], const u32 (&b)[8]) {
+  r[0] = add_cc(a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < 7; ++i) r[i] = addc_cc(a[i], b[i]);
+  r[7] = addc(a[7], b[7]);
+  cond_sub_mp<1>(r);
+}
+
+// add : field_arithmetic.cpp:172-182 for arbitrary 256-bit operands (carry out dropped, full reduce)
+__device__ __forceinline__ void fr_add_general(u32 (&r)[8], const u32 (&a)[8], const u32 (&b)[8]) {
+  r[0] = add_cc(a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < 7; ++i) r[i] = addc_cc(a[i], b[i]);
+  r[7] = addc(a[7], b[7]);
+  fr_reduce(r);
+}
+
+// subtract : field_arithmetic.cpp:184-219 restated on 64-bit limb semantics.
+// Works on u64 limbs because the reference's lost-borrow quirk is defined per 64-bit limb.
+__device__ __forceinline__ void fr_sub_ref(u64 (&r)[4], const u64 (&a)[4], const u64 (&b)[4]) {
+  const u64 p[4] = {0x43e1f593f0000001ULL, 0x2833e84879b97091ULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL};
+  bool lt = false, decided = false;  // a < b, most-significant limb first (:60-68)
+#pragma unroll
+  for (int i = 3; i >= 0; --i) {
+    if (!decided && a[i] != b[i]) { lt = a[i] < b[i]; decided = true; }
+  }
+  u64 x[4];
+  if (lt) {  // a + p mod 2^256 (:190-197)
+    u64 carry = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      u64 s = a[i] + p[i];
+      u64 c1 = s < a[i];
+      u64 s2 = s + carry;
+      u64 c2 = s2 < s;
+      x[i] = s2;
+      carry = c1 | c2;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = a[i];
+  }
+  u64 borrow = 0;  // subtract_internal (:204-219): b[i] + borrow wraps in 64 bits
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    u64 y = b[i] + borrow;
+    if (x[i] >= y) { r[i] = x[i] - y; borrow = 0; }
+    else { r[i] = x[i] - y; borrow = 1; }   // == x + (2^64-1 - y) + 1 mod 2^64
+  }
+}
+
+// ---- schoolbook products on even/odd 64-bit lanes ----
+// One row chain: acc[0..2*N-1] += {a0,a1,..} * b at lane stride 2, carry chained; returns nothing,
+// the carry out of the last lane is left in CC for the caller (addc) when needed.
+// NW = number of full (wide) lanes, LO = 1 when a final low-half-only product follows.
+template <int NW, int LO>
+__device__ __forceinline__ void row_chain(u32 *acc, const u32 *a /* stride 2 */, u32 b) {
+  if (NW > 0) {
+    acc[0] = mad_lo_cc(a[0], b, acc[0]);
+    acc[1] = madc_hi_cc(a[0], b, acc[1]);
+#pragma unroll
+    for (int j = 1; j < NW; ++j) {
+      acc[2 * j] = madc_lo_cc(a[2 * j], b, acc[2 * j]);
+      acc[2 * j + 1] = madc_hi_cc(a[2 * j], b, acc[2 * j + 1]);
+    }
+    if (LO) acc[2 * NW] = madc_lo(a[2 * NW], b, acc[2 * NW]);
+  } else if (LO) {
+    acc[0] = mad_lo(a[0], b, acc[0]);
+  }
+}
+
+// r[0..15] = a * b  (full 512-bit product)
+__device__ __forceinline__ void mul_wide_8x8(u32 (&r)[16], const u32 (&a)[8], const u32 (&b)[8]) {
+  u32 e[16], o[16];  // e[w]: word w from even-position products; o[w]: word w from odd-position products
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { e[i] = 0; o[i] = 0; }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if ((i & 1) == 0) {
+      row_chain<4, 0>(e + i, a, b[i]);            // a_even * b_i -> even positions i..i+6
+      if (i + 8 < 16) e[i + 8] = addc(0u, 0u);    // carry lands in a so-far untouched word
+      row_chain<4, 0>(o + i + 1, a + 1, b[i]);    // a_odd * b_i -> odd positions i+1..i+7 (no carry out)
+    } else {
+      row_chain<4, 0>(o + i, a, b[i]);
+      if (i + 8 < 16) o[i + 8] = addc(0u, 0u);
+      row_chain<4, 0>(e + i + 1, a + 1, b[i]);
+    }
+  }
+  r[0] = e[0];
+  r[1] = add_cc(e[1], o[1]);
+#pragma unroll
+  for (int i = 2; i < 15; ++i) r[i] = addc_cc(e[i], o[i]);
+  r[15] = addc(e[15], o[15]);
+}
+
+// t[0..7] = (t + a * b) mod 2^256   (low half only; 28 wide + 8 low products)
+__device__ __forceinline__ void mad_low_8x8(u32 (&t)[8], const u32 (&a)[8], const u32 (&b)[8]) {
+  u32 e[8], o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { e[i] = t[i]; o[i] = 0; }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    // positions i+j <= 7.  a_even: j = 0,2,4,6 ; a_odd: j = 1,3,5,7
+    if ((i & 1) == 0) {
+      // even positions i+j (j even): wide while i+j <= 6.
+      constexpr int dummy = 0; (void)dummy;
+      switch (i) {
+        case 0: row_chain<4, 0>(e + 0, a, b[0]); row_chain<3, 1>(o + 1, a + 1, b[0]); break;   // odd pos 1,3,5 wide, 7 lo
+        case 2: row_chain<3, 0>(e + 2, a, b[2]); row_chain<2, 1>(o + 3, a + 1, b[2]); break;   // even 2,4,6 ; odd 3,5 wide, 7 lo
+        case 4: row_chain<2, 0>(e + 4, a, b[4]); row_chain<1, 1>(o + 5, a + 1, b[4]); break;
+        case 6: row_chain<1, 0>(e + 6, a, b[6]); row_chain<0, 1>(o + 7, a + 1, b[6]); break;
+      }
+    } else {
+      switch (i) {
+        case 1: row_chain<3, 1>(o + 1, a, b[1]); row_chain<3, 0>(e + 2, a + 1, b[1]); break;   // odd pos 1,3,5 wide,7 lo ; even 2,4,6
+        case 3: row_chain<2, 1>(o + 3, a, b[3]); row_chain<2, 0>(e + 4, a + 1, b[3]); break;
+        case 5: row_chain<1, 1>(o + 5, a, b[5]); row_chain<1, 0>(e + 6, a + 1, b[5]); break;
+        case 7: row_chain<0, 1>(o + 7, a, b[7]); break;
+      }
+    }
+  }
+  t[0] = e[0];
+  t[1] = add_cc(e[1], o[1]);
+#pragma unroll
+  for (int i = 2; i < 7; ++i) t[i] = addc_cc(e[i], o[i]);
+  t[7] = addc(e[7], o[7]);
+}
+
+// reduce_512 : field_arithmetic.cpp:250-330 on a 16-word product.
+//   Mh = high*k ; t = (Mh_lo + (Mh_hi*k mod W)) mod W ; hc = Mh_hi != 0 ? reduce(t) : t ;
+//   r = reduce((low + hc) mod W)
+__device__ __forceinline__ void fr_reduce_512(u32 (&r)[8], const u32 (&prod)[16]) {
+  const u32 kk[8] = {CUZK_K0, CUZK_K1, CUZK_K2, CUZK_K3, CUZK_K4, CUZK_K5, CUZK_K6, CUZK_K7};
+  u32 high[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) high[i] = prod[8 + i];
+  u32 m1[16];
+  mul_wide_8x8(m1, high, kk);
+  u32 t[8], mh[8];
+  u32 mh_or = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { t[i] = m1[i]; mh[i] = m1[8 + i]; mh_or |= m1[8 + i]; }
+  mad_low_8x8(t, mh, kk);     // adds nothing when mh == 0, matching the reference's skip (:303)
+  if (mh_or != 0) fr_reduce(t);
+  r[0] = add_cc(prod[0], t[0]);
+#pragma unroll
+  for (int i = 1; i < 7; ++i) r[i] = addc_cc(prod[i], t[i]);
+  r[7] = addc(prod[7], t[7]);
+  fr_reduce(r);
+}
+
+// multiply : field_arithmetic.cpp:221-238 (valid for arbitrary 256-bit operands)
+__device__ __forceinline__ void fr_mul(u32 (&r)[8], const u32 (&a)[8], const u32 (&b)[8]) {
+  u32 prod[16];
+  mul_wide_8x8(prod, a, b);
+  fr_reduce_512(r, prod);
+}
+
+__device__ __forceinline__ void fr_sqr(u32 (&r)[8], const u32 (&a)[8]) { fr_mul(r, a, a); }
+
+// power5 : field_arithmetic.cpp:332-338
+__device__ __forceinline__ void fr_pow5(u32 (&r)[8], const u32 (&a)[8]) {
+  u32 a2[8], a4[8];
+  fr_sqr(a2, a);
+  fr_sqr(a4, a2);
+  fr_mul(r, a4, a);
+}
+
+}  // namespace cuzk

@@ -1,0 +1,150 @@
+/*
+ * cuzk_b200.h -- C ABI of the B200-native cuZK hot path (libcuzk_b200.so).
+ *
+ * The reference (davencyw/cuZK) has no C ABI: its boundary is a set of C++ classes that tests
+ * and benchmarks include directly.  Each entry point below names the reference interface it
+ * replaces (file:line under the reference tree).  The C++ host classes with the reference's own
+ * names (cuzk_b200/host/) are thin wrappers over these functions; INTEGRATION.md shows the
+ * binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - Field elements: 4 x uint64_t little-endian limbs, plain canonical form, 32 bytes, i.e. the
+ *     memory layout of `struct FieldElement` (src/poseidon/field_arithmetic.hpp:11-14) and of
+ *     `CudaFieldElement` (src/poseidon/cuda/cuda_field_element.cuh:13-113).  Arrays are packed AoS.
+ *   - `mem`: CUZK_MEM_DEVICE = every pointer is device memory on the current CUDA device and the
+ *     call is asynchronous on `stream`; CUZK_MEM_HOST = every pointer is host memory, the library
+ *     stages through its own device buffers and returns after the results are in the host buffer.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - Return value: CUZK_OK (0) or a negative error code; cuzk_last_error() gives a message
+ *     (thread-local).  Nothing throws, nothing calls exit, there is NO CPU fallback: without a
+ *     usable GPU every compute call fails with CUZK_ERR_CUDA.
+ *   - Results are bit-exact with the reference CPU implementation (including its non-standard
+ *     512->256-bit reduction); see DESIGN.md.
+ */
+#ifndef CUZK_B200_H
+#define CUZK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CUZK_OK 0
+#define CUZK_ERR_INVALID (-1) /* bad argument (arity outside 2..8, NULL pointer with n > 0, ...) */
+#define CUZK_ERR_CUDA (-2)    /* CUDA runtime error, no device, or library not initialised */
+#define CUZK_ERR_CONSTANTS (-3) /* generated round constants do not fit the compiled-in fast path */
+
+#define CUZK_MEM_DEVICE 0
+#define CUZK_MEM_HOST 1
+
+/* element-wise field operations, reference: CudaFieldArithmetic::batch_{add,subtract,multiply,square,power5}
+ * (src/poseidon/cuda/field_arithmetic_cuda.cuh:34-51) */
+#define CUZK_FR_ADD 0
+#define CUZK_FR_SUB 1
+#define CUZK_FR_MUL 2
+#define CUZK_FR_SQR 3
+#define CUZK_FR_POW5 4
+
+/* ---- lifecycle: CudaFieldArithmetic::initialize/cleanup (field_arithmetic_cuda.cuh:28-31),
+ *      CudaPoseidonHash ctor/dtor (poseidon_cuda.cuh:26-27), CudaNaryMerkleTree::initialize_cuda/cleanup_cuda
+ *      (merkle_tree_cuda.cuh:101-102).  Reference-counted and idempotent; never resets the device. ---- */
+int cuzk_init(int device);
+int cuzk_shutdown(void);
+int cuzk_is_initialized(void);
+int cuzk_device_count(void); /* CudaFieldArithmetic::get_device_count (field_arithmetic_cuda.cuh:60) */
+const char *cuzk_last_error(void);
+const char *cuzk_version(void);
+/* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
+uint64_t cuzk_launch_count(void);
+
+/* ---- Fr batch ops (out[i] = op(a[i], b[i]); b ignored for SQR/POW5).  Inputs may be any 256-bit values. ---- */
+int cuzk_fr_batch(int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n, int mem, void *stream);
+
+/* ---- Poseidon batch hashing: IPoseidonCudaHash (src/poseidon/cuda/poseidon_interface_cuda.hpp:27-47) ---- */
+/* batch_hash_single (:32-33): out[i] = PoseidonHash::hash_single(in[i])   (poseidon.cpp:89-91) */
+int cuzk_poseidon_hash_single(const uint64_t *in, uint64_t *out, size_t n, int mem, void *stream);
+/* batch_hash_pairs (:35-37): out[i] = PoseidonHash::hash_pair(left[i], right[i])   (poseidon.cpp:93-96) */
+int cuzk_poseidon_hash_pairs(const uint64_t *left, const uint64_t *right, uint64_t *out, size_t n, int mem,
+                             void *stream);
+/* batch_permutation (:39): in-place PoseidonHash::permutation on n states of 3 elements (poseidon.cpp:60-87) */
+int cuzk_poseidon_permutation(uint64_t *states, size_t n, int mem, void *stream);
+/* out[i] = PoseidonHash::sponge(in[i*width .. i*width+width-1], FieldElement(domain_sep))  (poseidon.cpp:103-126);
+ * domain_sep 3 = hash_multiple (:98-101) = device_hash_n (src/poseidon/cuda/poseidon_cuda.cu:118-142). width <= 64. */
+int cuzk_poseidon_sponge(const uint64_t *in, size_t width, uint64_t domain_sep, uint64_t *out, size_t n, int mem,
+                         void *stream);
+/* round constants (192 x 4 limbs) and MDS matrix (9 x 4 limbs) as the library uses them; host output.
+ * PoseidonConstants::ROUND_CONSTANTS / MDS_MATRIX (src/poseidon/poseidon.hpp:19-40) */
+int cuzk_poseidon_constants(uint64_t *round_constants_out, uint64_t *mds_out);
+
+/* ---- Merkle geometry (pure host arithmetic) ---- */
+/* leaf level padded to arity^L >= n (merkle_tree.cpp:50-53) */
+size_t cuzk_merkle_padded_leaves(size_t n, unsigned arity);
+/* number of level arrays, leaf level and root included; 0 for n == 0 (integer loop of merkle_tree.cpp:66-97) */
+size_t cuzk_merkle_num_levels(size_t n, unsigned arity);
+/* sum of the sizes of all padded levels */
+size_t cuzk_merkle_total_nodes(size_t n, unsigned arity);
+/* NaryMerkleTree::calculate_tree_height (merkle_tree.cpp:359-367): the reference's floating-point
+ * formula, for the get_tree_height() getter only -- never used to size anything */
+size_t cuzk_merkle_tree_height(size_t leaf_count, unsigned arity);
+
+/* NaryMerkleTree::compute_empty_hash (merkle_tree.cpp:347-357), computed on the GPU; host output */
+int cuzk_merkle_empty_hash(unsigned arity, uint64_t out[4]);
+
+/* CudaNaryMerkleTree::build_tree (src/merkle_tree/merkle_tree_cuda.cuh:67, merkle_tree_cuda.cu:141-259) /
+ * NaryMerkleTree::build_tree (merkle_tree.cpp:29-100).  Writes every level, level-major:
+ * level 0 = the n leaves (un-hashed) padded with empty_hash to padded_leaves, ..., last = root;
+ * levels_out holds cuzk_merkle_total_nodes(n, arity) elements.  n >= 1. */
+int cuzk_merkle_build(const uint64_t *leaves, size_t n, unsigned arity, uint64_t *levels_out, int mem,
+                      void *stream);
+
+/* Subtree-root pass (the multi-GPU shard step, and the "only roots reach HBM" build): the `n` given leaves
+ * are the first leaves of `count` consecutive subtrees of arity^height padded leaves each
+ * (n <= count * arity^height; the tail is virtual padding).  roots_out[i] = root of subtree i, where
+ * all-padding subtrees get the level-`height` padding constant.  No intermediate level is stored. */
+int cuzk_merkle_subtree_roots(const uint64_t *leaves, size_t n, unsigned arity, unsigned height, size_t count,
+                              uint64_t *roots_out, int mem, void *stream);
+
+/* Root of the tree whose level-`base_level` nodes are given (`count` = a power of arity of them; all of them real):
+ * hashes upward with hash_multiple and writes the single root.  Used for the top levels above the per-GPU
+ * subtree roots. */
+int cuzk_merkle_top_root(const uint64_t *nodes, size_t count, unsigned arity, uint64_t *root_out, int mem,
+                         void *stream);
+
+/* the constant root of an all-padding subtree of `height` levels: E_0 = empty_hash(arity),
+ * E_{l+1} = hash_multiple(arity copies of E_l); host output */
+int cuzk_merkle_padding_root(unsigned arity, unsigned height, uint64_t out[4]);
+
+/* CudaNaryMerkleTree::generate_batch_proofs (merkle_tree_cuda.cuh:74, merkle_tree_cuda.cu:261-339) /
+ * NaryMerkleTree::generate_proof (merkle_tree.cpp:113-211) on the level arrays produced by cuzk_merkle_build.
+ * For proof q of leaf indices[q] (< n) and level l (0 = leaf level, num_levels-1 of them):
+ *   positions_out[q*L + l]                        = (indices[q] / arity^l) mod arity      (MerkleProof::indices)
+ *   siblings_out[(q*L + l)*(arity-1) + s]         = the s-th other child of that group     (MerkleProof::path)
+ * An index >= n yields positions 0xFFFFFFFF for that proof (the reference returns std::nullopt). */
+int cuzk_merkle_prove_batch(const uint64_t *levels, size_t n, unsigned arity, const uint64_t *indices,
+                            size_t num_proofs, uint64_t *siblings_out, uint32_t *positions_out, int mem,
+                            void *stream);
+
+/* CudaNaryMerkleTree::verify_batch_proofs (merkle_tree_cuda.cuh:75-76, merkle_tree_cuda.cu:341-465) /
+ * NaryMerkleTree::verify_proof (merkle_tree.cpp:214-254): results_out[q] = 1 when folding leaf q up
+ * `levels` levels with hash_multiple reproduces `root`, 0 otherwise (also 0 when a position >= arity). */
+int cuzk_merkle_verify_batch(const uint64_t *leaf_values, const uint64_t *siblings, const uint32_t *positions,
+                             size_t levels, unsigned arity, const uint64_t *root, uint8_t *results_out,
+                             size_t num_proofs, int mem, void *stream);
+
+/* ---- synthetic inputs: generated on the device so multi-GiB leaf sets need no upload.
+ * element i, limb j = splitmix64(seed, 4*(start+i)+j), top limb masked to 60 bits when canonical != 0;
+ * u64 leaves: limb 0 = splitmix64(seed, start+i), other limbs 0.  Device pointers only. ---- */
+int cuzk_synth_elements(uint64_t *out, size_t n, uint64_t seed, uint64_t start, int canonical, void *stream);
+int cuzk_synth_u64_leaves(uint64_t *out, size_t n, uint64_t seed, uint64_t start, void *stream);
+
+/* integer-multiply pipe microbenchmark: runs `iters` rounds of dependent-free IMAD.WIDE chains on the whole
+ * chip and returns measured 32x32->64 multiply-adds per second (the roofline denominator); variant selects
+ * 0 = IMAD.WIDE.U32, 1 = IMAD (lo) 2 = IMAD.HI, 3 = IMAD.WIDE.U32.X carry chains, 4 = IADD3 */
+int cuzk_imad_peak(int variant, int iters, double *ops_per_second_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUZK_B200_H */

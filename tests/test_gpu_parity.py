@@ -1,0 +1,273 @@
+"""GPU parity tests (run with -m gpu on a B200): every result produced through the C ABI is compared
+bit-for-bit with the oracle on the same seeded inputs and with the committed golden fixtures."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from helpers import h2a, rnd, to_dev, to_host
+from oracle_lib import K_INT, P_INT, hexes, ints_to_array, synth_elements, synth_u64_leaves
+from test_oracle import mt19937_64_leaves
+
+pytestmark = pytest.mark.gpu
+
+EDGE = ints_to_array([0, 1, 2, P_INT - 1, P_INT, P_INT + 1, 2 * P_INT, 5 * P_INT, 5 * P_INT + 1, 2**256 - 1, 2**128 - 1, 2**255, K_INT,
+                      2**256 - 2**64, 2**64 - 1, (1 << 192) + (5 << 64), 1 + ((2**64 - 1) << 64), 2**224 - 1])
+
+
+def _ops(api):
+    F = api.CudaFieldArithmetic
+    return {"add": F.batch_add, "sub": F.batch_subtract, "mul": F.batch_multiply, "sqr": lambda a, b: F.batch_square(a),
+            "pow5": lambda a, b: F.batch_power5(a)}
+
+
+def test_native_library_is_loaded(gpu):
+    from cuzk_b200 import lib
+
+    before = lib.get_lib().cuzk_launch_count()
+    gpu.CudaFieldArithmetic.batch_add(EDGE, EDGE)
+    assert lib.get_lib().cuzk_launch_count() > before
+    assert lib.LIB_PATH in open("/proc/self/maps").read()
+
+
+def test_constants_match_oracle(gpu, oracle):
+    rc, mds = gpu.CudaPoseidonHash.constants()
+    assert (rc == oracle.round_constants()).all()
+    assert (mds == oracle.mds()).all()
+
+
+@pytest.mark.parametrize("where", ["host", "device"])
+def test_field_ops_golden(gpu, where):
+    g = load_golden("fr_ops.json")
+    a, b = h2a(g["a"]), h2a(g["b"])
+    for op, fn in _ops(gpu).items():
+        got = fn(a, b) if where == "host" else to_host(fn(to_dev(a), to_dev(b)))
+        assert hexes(got) == g[op], op
+
+
+@pytest.mark.parametrize("canonical", [True, False])
+def test_field_ops_random_vs_oracle(gpu, oracle, canonical):
+    rng = np.random.default_rng(100 + canonical)
+    n = 200_000
+    a = np.concatenate([rnd(rng, n, canonical), EDGE, EDGE[::-1]])
+    b = np.concatenate([rnd(rng, n, canonical), EDGE[::-1], EDGE])
+    da, db = to_dev(a), to_dev(b)
+    for op, fn in _ops(gpu).items():
+        m = n if op in ("add", "sub") else (n if op != "pow5" else 60_000)
+        sel = np.r_[0:m, n : a.shape[0]]
+        got = to_host(fn(da, db))[sel]
+        want = oracle.batch_fr(op, a[sel], b[sel])
+        bad = np.nonzero((got != want).any(axis=1))[0]
+        assert bad.size == 0, (op, canonical, bad[:5], hexes(a[sel][bad[:1]]), hexes(b[sel][bad[:1]]))
+
+
+def test_field_small_operands(gpu, oracle):
+    """mh == 0 / high == 0 paths of reduce_512 (small operands, as in the first rounds of hash_single(0))."""
+    vals = [0, 1, 2, 3, 5, 2**32 - 1, 2**32, 2**64 - 1, 2**64, 2**96 + 12345, 2**127, 2**128 - 1, 2**129, 2**160 + 7, 2**192 - 1]
+    a = ints_to_array([x for x in vals for _ in vals])
+    b = ints_to_array([y for _ in vals for y in vals])
+    for op, fn in _ops(gpu).items():
+        assert (fn(a, b) == oracle.batch_fr(op, a, b)).all(), op
+
+
+def test_poseidon_golden(gpu):
+    g = load_golden("poseidon.json")
+    h = gpu.CudaPoseidonHash()
+    assert hexes(h.batch_hash_single(h2a(g["single_in"]))) == g["single_out"]
+    assert hexes(h.batch_hash_pairs(h2a(g["pair_l"]), h2a(g["pair_r"]))) == g["pair_out"]
+    st = h2a(g["perm_in"]).reshape(-1, 3, 4).copy()
+    assert hexes(h.batch_permutation(st).reshape(-1, 4)) == g["perm_out"]
+    for case in g["sponge"]:
+        got = h.batch_sponge(h2a(case["in"]), case["width"], case["ds"])
+        assert hexes(got) == case["out"], (case["width"], case["ds"])
+    for a, want in g["empty_hash"].items():
+        assert hexes(gpu.empty_hash(int(a)))[0] == want
+
+
+def test_poseidon_random_vs_oracle(gpu, oracle):
+    rng = np.random.default_rng(5)
+    h = gpu.CudaPoseidonHash()
+    n = 3000
+    x = np.concatenate([rnd(rng, n, False), EDGE])
+    y = np.concatenate([rnd(rng, n, True), EDGE[::-1]])
+    assert (to_host(h.batch_hash_single(to_dev(x))) == oracle.hash_single(x)).all()
+    assert (to_host(h.batch_hash_pairs(to_dev(x), to_dev(y))) == oracle.hash_pairs(x, y)).all()
+    assert (h.batch_hash_pairs(x, y) == oracle.hash_pairs(x, y)).all()  # host-pointer path
+    st = rnd(rng, 3 * 1000, False).reshape(-1, 3, 4)
+    assert (to_host(h.batch_permutation(to_dev(st.reshape(-1, 4)))).reshape(-1, 3, 4) == oracle.permutation(st)).all()
+    for width in (1, 2, 3, 4, 5, 7, 8):
+        z = rnd(rng, 200 * width, False)
+        assert (to_host(h.batch_sponge(to_dev(z), width, 3)) == oracle.sponge(z, width, 3)).all(), width
+
+
+def test_reference_test_inputs(gpu, oracle):
+    """The inputs verify_cuda_implementations_match uses (poseidon_cuda_benchmarks.cpp:137-259) and the
+    sequential inputs of PoseidonCUDATest (test_poseidon_cuda.cpp:90-110)."""
+    h = gpu.CudaPoseidonHash()
+    i = np.arange(100, dtype=np.uint64)
+    single = np.stack([i + 1, 2 * i + 1, 3 * i + 1, 4 * i + 1], axis=1).astype(np.uint64)
+    right = np.stack([5 * i + 1, 6 * i + 1, 7 * i + 1, 8 * i + 1], axis=1).astype(np.uint64)
+    assert (h.batch_hash_single(single) == oracle.hash_single(single)).all()
+    assert (h.batch_hash_pairs(single, right) == oracle.hash_pairs(single, right)).all()
+    seq = np.zeros((10000, 4), dtype=np.uint64)
+    seq[:, 0] = np.arange(10000)
+    got = h.batch_hash_single(seq)
+    pick = np.r_[0:50, 5000:5050, 9950:10000]
+    assert (got[pick] == oracle.hash_single(seq[pick])).all()
+
+
+def test_empty_and_mismatched_batches(gpu):
+    h = gpu.CudaPoseidonHash()
+    z = np.zeros((0, 4), dtype=np.uint64)
+    assert h.batch_hash_single(z).shape == (0, 4)
+    assert h.batch_hash_pairs(z, z).shape == (0, 4)
+    with pytest.raises(Exception):
+        h.batch_hash_pairs(np.zeros((3, 4), dtype=np.uint64), np.zeros((2, 4), dtype=np.uint64))
+    with pytest.raises(Exception):
+        gpu.CudaFieldArithmetic.batch_add(np.zeros((3, 4), dtype=np.uint64), np.zeros((2, 4), dtype=np.uint64))
+    with pytest.raises(ValueError):
+        gpu.CudaNaryMerkleTree(arity=1)
+    with pytest.raises(ValueError):
+        gpu.CudaNaryMerkleTree(arity=10)
+
+
+def test_pair_hash_synthetic_stream_and_determinism(gpu, oracle):
+    """Config 1 inputs (seeded splitmix64 stream): device generator == host generator, GPU == oracle on a sample,
+    and two runs agree bit-for-bit at the full 1M size."""
+    import torch
+
+    from cuzk_b200 import lib
+
+    L = lib.get_lib()
+    n = 1_000_000
+    dl = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+    dr = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+    L.check(L.cuzk_synth_elements(dl.data_ptr(), n, 1, 0, 1, None), "synth")
+    L.check(L.cuzk_synth_elements(dr.data_ptr(), n, 2, 0, 1, None), "synth")
+    assert (to_host(dl[:1000]) == synth_elements(1, 1000)).all()
+    assert (to_host(dr[-1000:]) == synth_elements(2, 1000, start=n - 1000)).all()
+    h = gpu.CudaPoseidonHash()
+    o1 = h.batch_hash_pairs(dl, dr)
+    o2 = h.batch_hash_pairs(dl, dr)
+    assert torch.equal(o1, o2)
+    pick = torch.cat([torch.arange(0, 2000), torch.arange(n - 2000, n), torch.randint(0, n, (2000,))]).cuda()
+    want = oracle.hash_pairs(to_host(dl[pick]), to_host(dr[pick]))
+    assert (to_host(o1[pick]) == want).all()
+    # canonical outputs
+    top = to_host(o1)[:, 3]
+    assert (top <= np.uint64(0x30644E72E131A029)).all()
+
+
+# ---------------------------------------------------------------- Merkle ----
+def test_merkle_golden(gpu):
+    g = load_golden("merkle.json")
+    for ent in g["trees"]:
+        leaves = h2a(ent["leaves"]) if "leaves" in ent else mt19937_64_leaves(ent["n"], 42)
+        t = gpu.CudaNaryMerkleTree(leaves, arity=ent["arity"])
+        assert hexes(t.get_root_hash())[0] == ent["root"], (ent["arity"], ent["n"])
+        assert t.get_tree_height() == ent["height"]
+        if ent["proofs"] and ent["n"] > 1:
+            idx = [p["index"] for p in ent["proofs"]]
+            pb = t.generate_batch_proofs(idx)
+            for k, p in enumerate(ent["proofs"]):
+                assert [int(v) for v in pb.positions[k]] == p["positions"]
+                assert hexes(pb.siblings[k].reshape(-1, 4)) == p["siblings"]
+    for a, want in g["empty_root"].items():
+        assert hexes(gpu.CudaNaryMerkleTree(arity=int(a)).get_root_hash())[0] == want
+
+
+@pytest.mark.parametrize("arity", [2, 3, 4, 5, 6, 7, 8])
+def test_merkle_levels_proofs_verify_vs_oracle(gpu, oracle, arity):
+    rng = np.random.default_rng(arity)
+    for n in (1, 2, arity, arity + 1, arity**2, arity**2 + 1, 100, 257, 1000):
+        leaves = rnd(rng, n, False) if n % 2 else synth_u64_leaves(9, n)
+        want = oracle.merkle_build(leaves, arity)
+        for dev in (False, True):
+            t = gpu.CudaNaryMerkleTree(to_dev(leaves) if dev else leaves, arity=arity)
+            levels = [to_host(x) if dev else x for x in t.get_tree_levels()]
+            assert len(levels) == len(want)
+            for l, (gl, wl) in enumerate(zip(levels, want)):
+                assert (gl == wl).all(), (arity, n, dev, l)
+            if n == 1:
+                continue
+            idx = np.unique(np.r_[0, n - 1, rng.integers(0, n, size=min(n, 40))])
+            pb = t.generate_batch_proofs(to_dev(idx.astype(np.int64)) if dev else idx)
+            sib = to_host(pb.siblings) if dev else pb.siblings
+            pos = pb.positions.cpu().numpy().view(np.uint32) if dev else pb.positions
+            for k, i in enumerate(idx):
+                so, po = oracle.merkle_prove(want, n, arity, int(i))
+                assert (sib[k] == so).all() and (pos[k] == po.astype(np.uint32)).all()
+            lv = leaves[idx]
+            res = t.verify_batch_proofs(pb, to_dev(lv) if dev else lv)
+            res = res.cpu().numpy() if dev else res
+            assert res.all()
+            # corrupted leaf / sibling / position / root must fail exactly like the oracle
+            bad_leaf = lv.copy()
+            bad_leaf[0, 0] ^= np.uint64(1)
+            r2 = t.verify_batch_proofs(pb, to_dev(bad_leaf) if dev else bad_leaf)
+            r2 = r2.cpu().numpy() if dev else r2
+            assert r2[0] == 0 and r2[1:].all()
+            if not dev:
+                sib2 = pb.siblings.copy()
+                sib2[-1, -1, 0, 3] ^= np.uint64(1 << 40)
+                pos2 = pb.positions.copy()
+                pos2[0, 0] = (pos2[0, 0] + 1) % arity
+                pb2 = gpu.MerkleProofBatch(sib2, pos2, idx, arity)
+                r3 = t.verify_batch_proofs(pb2, lv)
+                want3 = [oracle.merkle_verify(lv[k], sib2[k], pos2[k].astype(np.uint64), arity, want[-1][0]) for k in range(len(idx))]
+                assert [bool(v) for v in r3] == want3
+                pos3 = pb.positions.copy()
+                pos3[0, -1] = arity  # out-of-range position -> false (merkle_tree.cpp:228-230)
+                r4 = t.verify_batch_proofs(gpu.MerkleProofBatch(pb.siblings, pos3, idx, arity), lv)
+                assert r4[0] == 0 and r4[1:].all()
+            # out-of-range index -> sentinel positions (reference: std::nullopt)
+            if not dev:
+                pbo = t.generate_batch_proofs(np.array([n, 0], dtype=np.uint64))
+                assert (pbo.positions[0] == 0xFFFFFFFF).all() and (pbo.positions[1] != 0xFFFFFFFF).all()
+
+
+def test_config2_binary_50k_leaves_5k_proofs(gpu, oracle):
+    """BASELINE config: binary tree over 50 000 leaves (generate_test_leaves seed 0) + 5 000 proof verifications."""
+    n, arity = 50_000, 2
+    leaves = mt19937_64_leaves(n, 0)
+    t = gpu.CudaNaryMerkleTree(to_dev(leaves), arity=arity)
+    levels = [to_host(x) for x in t.get_tree_levels()]
+    assert len(levels) == 17 and levels[0].shape[0] == 65536
+    # level 1 in full and every upper level against the oracle's hashing of OUR lower level (chain of custody)
+    for l in range(1, len(levels)):
+        m = levels[l].shape[0]
+        sel = np.arange(m) if m <= 4096 else np.unique(np.r_[0:1024, m - 1024 : m, np.random.default_rng(l).integers(0, m, 2048)])
+        kids = levels[l - 1].reshape(m, arity, 4)[sel].reshape(-1, 4)
+        assert (levels[l][sel] == oracle.sponge(kids, arity, 3)).all(), l
+    idx = (np.arange(5000, dtype=np.uint64) * 10) % n
+    pb = t.generate_batch_proofs(to_dev(idx.astype(np.int64)))
+    res = t.verify_batch_proofs(pb, to_dev(leaves[idx]))
+    assert bool(res.all())
+    k = 17
+    so, po = oracle.merkle_prove(levels, n, arity, int(idx[k]))
+    assert (to_host(pb.siblings[k]) == so).all()
+    assert oracle.merkle_verify(leaves[idx[k]], so, po, arity, levels[-1][0])
+
+
+def test_subtree_roots_and_top_equal_full_build(gpu, oracle):
+    """The multi-GPU decomposition on one GPU: per-shard subtree roots + top levels == full build root."""
+    import torch
+
+    from cuzk_b200 import lib
+
+    L = lib.get_lib()
+    for arity, n, height in ((8, 8**3, 2), (8, 300, 2), (4, 4**4, 2), (4, 200, 3), (2, 1000, 5), (3, 81, 2), (5, 30, 1)):
+        leaves = synth_u64_leaves(4, n)
+        want_root = oracle.merkle_build(leaves, arity)[-1][0]
+        padded = gpu.padded_leaves(n, arity)
+        span = arity**height
+        count = padded // span
+        d = to_dev(leaves)
+        roots = torch.empty((count, 4), dtype=torch.int64, device="cuda")
+        L.check(L.cuzk_merkle_subtree_roots(d.data_ptr(), n, arity, height, count, roots.data_ptr(), 0, None), "subtree_roots")
+        root = torch.empty((1, 4), dtype=torch.int64, device="cuda")
+        L.check(L.cuzk_merkle_top_root(roots.data_ptr(), count, arity, root.data_ptr(), 0, None), "top_root")
+        assert (to_host(root)[0] == want_root).all(), (arity, n, height)
+        # all-padding subtrees carry the padding constant of that level
+        real = -(-n // span)
+        if real < count:
+            assert (to_host(roots[real:]) == gpu.padding_root(arity, height)).all()
