@@ -323,67 +323,6 @@ __global__ void synth_u64_leaves_kernel(u64 *out, size_t n, u64 seed, u64 start)
   reinterpret_cast<ulonglong4 *>(out)[i] = make_ulonglong4(splitmix64_dev(seed, start + i), 0, 0, 0);
 }
 
-// ---- integer-pipe microbenchmark (roofline denominator) ----
-template <int VARIANT>
-__global__ void __launch_bounds__(256) imad_peak_kernel(u32 *sink, int iters, u32 seed) {
-  // 16 independent accumulator lanes per thread; each loop trip issues 16 multiply-adds per lane group
-  u32 lo[16], hi[16];
-  u32 a = seed + threadIdx.x * 2654435761u + 1u, b = seed * 40503u + blockIdx.x + 3u;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) { lo[i] = a + i; hi[i] = b ^ i; }
-#pragma unroll 1
-  for (int it = 0; it < iters; ++it) {
-#pragma unroll
-    for (int rep = 0; rep < 4; ++rep) {
-      if (VARIANT == 0) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) mad_wide(lo[i], hi[i], a, b);
-      } else if (VARIANT == 1) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) lo[i] = lo[i] * a + hi[i];
-      } else if (VARIANT == 2) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) lo[i] = __umulhi(lo[i], a) + hi[i];
-      } else if (VARIANT == 3) {
-        // four independent carry chains of four wide mads each
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          lo[4 * c] = mad_lo_cc(a, b, lo[4 * c]);
-          hi[4 * c] = madc_hi_cc(a, b, hi[4 * c]);
-#pragma unroll
-          for (int j = 1; j < 4; ++j) {
-            lo[4 * c + j] = madc_lo_cc(a, b, lo[4 * c + j]);
-            hi[4 * c + j] = madc_hi_cc(a, b, hi[4 * c + j]);
-          }
-          a = addc(a, 0u);
-        }
-      } else if (VARIANT == 4) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) asm volatile("add.u32 %0, %0, %1;" : "+r"(lo[i]) : "r"(hi[i]));
-      } else if (VARIANT == 5) {
-        // 1:1 mix: a wide mad and an independent add per lane
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          mad_wide(lo[i], hi[i], a, b);
-          asm volatile("add.u32 %0, %0, %1;" : "+r"(lo[8 + i]) : "r"(hi[8 + i]));
-        }
-      } else if (VARIANT == 6) {
-        // 1:2 mix: a wide mad and two adds
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-          mad_wide(lo[i], hi[i], a, b);
-          asm volatile("add.u32 %0, %0, %1;" : "+r"(lo[5 + i]) : "r"(hi[5 + i]));
-          asm volatile("add.u32 %0, %0, %1;" : "+r"(lo[10 + i]) : "r"(hi[10 + i]));
-        }
-      }
-    }
-  }
-  u32 acc = a;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) acc ^= lo[i] ^ hi[i];
-  if (acc == 0x12345u) sink[0] = acc;  // practically never true; keeps the chains live
-}
-
 // ------------------------------------------------------------------------------------------------
 // host helpers
 // ------------------------------------------------------------------------------------------------
@@ -882,47 +821,6 @@ int cuzk_synth_u64_leaves(uint64_t *out, size_t n, uint64_t seed, uint64_t start
   if (n == 0) return CUZK_OK;
   synth_u64_leaves_kernel<<<grid_for(n, 256), 256, 0, S(stream)>>>(out, n, seed, start);
   return check_launch("synth_u64_leaves_kernel");
-}
-
-int cuzk_imad_peak(int variant, int iters, double *ops_per_second_out) {
-  int dev = 0;
-  CK(cudaGetDevice(&dev));
-  cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, dev));
-  const int blocks = prop.multiProcessorCount * 8, threads = 256;
-  DevBuf sink;
-  CK(sink.alloc(4));
-  cudaEvent_t e0, e1;
-  CK(cudaEventCreate(&e0));
-  CK(cudaEventCreate(&e1));
-  float best = 1e30f;
-  for (int rep = 0; rep < 4; ++rep) {
-    CK(cudaEventRecord(e0));
-    switch (variant) {
-      case 0: imad_peak_kernel<0><<<blocks, threads>>>(sink.as<u32>(), iters, 1u + rep); break;
-      case 1: imad_peak_kernel<1><<<blocks, threads>>>(sink.as<u32>(), iters, 1u + rep); break;
-      case 2: imad_peak_kernel<2><<<blocks, threads>>>(sink.as<u32>(), iters, 1u + rep); break;
-      case 3: imad_peak_kernel<3><<<blocks, threads>>>(sink.as<u32>(), iters, 1u + rep); break;
-      case 4: imad_peak_kernel<4><<<blocks, threads>>>(sink.as<u32>(), iters, 1u + rep); break;
-      case 5: imad_peak_kernel<5><<<blocks, threads>>>(sink.as<u32>(), iters, 1u + rep); break;
-      case 6: imad_peak_kernel<6><<<blocks, threads>>>(sink.as<u32>(), iters, 1u + rep); break;
-      default: return fail(CUZK_ERR_INVALID, "unknown variant");
-    }
-    int rc = check_launch("imad_peak_kernel");
-    if (rc) return rc;
-    CK(cudaEventRecord(e1));
-    CK(cudaEventSynchronize(e1));
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, e0, e1));
-    if (rep > 0 && ms < best) best = ms;
-  }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  // multiply-adds (or adds) per thread per trip: variants 0-4: 64; 5: 32 mads (+32 adds); 6: 20 mads (+40 adds)
-  double per_trip = variant == 5 ? 32.0 : variant == 6 ? 20.0 : 64.0;
-  double total = per_trip * (double)iters * (double)blocks * (double)threads;
-  *ops_per_second_out = total / (best * 1e-3);
-  return CUZK_OK;
 }
 
 }  // extern "C"

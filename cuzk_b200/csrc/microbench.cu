@@ -1,0 +1,141 @@
+// microbench.cu -- integer-pipe microbenchmarks that give the roofline its denominator (cuzk_imad_peak).
+//
+// Every variant keeps 16 independent accumulator lanes per thread, 2048 threads per SM, and makes each
+// multiply depend on its own previous result so nothing is loop-invariant.  Rates are reported as
+// operations per second over the whole chip.
+#include <cuda_runtime.h>
+
+#include "../../include/cuzk_b200.h"
+#include "fr.cuh"
+
+using namespace cuzk;
+
+template <int VARIANT>
+__global__ void __launch_bounds__(256) imad_peak_kernel(u32 *sink, int iters, u32 seed) {
+  u32 lo[16], hi[16];
+  u32 b = seed * 40503u + blockIdx.x * 2u + 3u;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { lo[i] = seed + threadIdx.x * 2654435761u + i; hi[i] = b ^ (i * 0x9E3779B9u); }
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int rep = 0; rep < 4; ++rep) {
+      if (VARIANT == 0) {          // IMAD.WIDE.U32: (hi:lo) = lo * b + (hi:lo)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) mad_wide(lo[i], hi[i], lo[i], b);
+      } else if (VARIANT == 1) {   // IMAD (low 32 bits)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) lo[i] = lo[i] * b + hi[i];
+      } else if (VARIANT == 2) {   // IMAD.HI.U32
+#pragma unroll
+        for (int i = 0; i < 16; ++i) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(lo[i]) : "r"(b), "r"(hi[i]));
+      } else if (VARIANT == 3) {   // IMAD.WIDE.U32.X: four independent carry chains of four lanes (as in mul_wide_8x8)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          lo[4 * c] = mad_lo_cc(lo[4 * c], b, lo[4 * c]);
+          hi[4 * c] = madc_hi_cc(lo[4 * c], b, hi[4 * c]);
+#pragma unroll
+          for (int j = 1; j < 4; ++j) {
+            const u32 m = hi[4 * c + j - 1];
+            lo[4 * c + j] = madc_lo_cc(m, b, lo[4 * c + j]);
+            hi[4 * c + j] = madc_hi_cc(m, b, hi[4 * c + j]);
+          }
+        }
+      } else if (VARIANT == 4) {   // IADD3.X carry chains: two chains of eight
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          lo[8 * c] = add_cc(lo[8 * c], hi[8 * c]);
+#pragma unroll
+          for (int j = 1; j < 7; ++j) lo[8 * c + j] = addc_cc(lo[8 * c + j], hi[8 * c + j]);
+          lo[8 * c + 7] = addc(lo[8 * c + 7], hi[8 * c + 7]);
+        }
+      } else if (VARIANT == 5) {   // 8 wide mads + 8 carry-chain adds (1:1)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mad_wide(lo[i], hi[i], lo[i], b);
+        lo[8] = add_cc(lo[8], hi[8]);
+#pragma unroll
+        for (int j = 9; j < 15; ++j) lo[j] = addc_cc(lo[j], hi[j]);
+        lo[15] = addc(lo[15], hi[15]);
+      } else if (VARIANT == 6) {   // 8 wide mads + 16 carry-chain adds (1:2)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mad_wide(lo[i], hi[i], lo[i], b);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          lo[8] = add_cc(lo[8], hi[8]);
+#pragma unroll
+          for (int j = 9; j < 15; ++j) lo[j] = addc_cc(lo[j], hi[j]);
+          lo[15] = addc(lo[15], hi[15]);
+        }
+      } else if (VARIANT == 7) {   // 8 wide mads + 24 carry-chain adds (1:3)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mad_wide(lo[i], hi[i], lo[i], b);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          lo[8] = add_cc(lo[8], hi[8]);
+#pragma unroll
+          for (int j = 9; j < 15; ++j) lo[j] = addc_cc(lo[j], hi[j]);
+          lo[15] = addc(lo[15], hi[15]);
+        }
+      } else if (VARIANT == 8) {   // SEL
+#pragma unroll
+        for (int i = 0; i < 16; ++i) asm volatile("{.reg .pred p; setp.ne.u32 p, %1, 0; selp.u32 %0, %0, %2, p;}" : "+r"(lo[i]) : "r"(b), "r"(hi[i]));
+      } else if (VARIANT == 9) {   // DFMA (FP64 pipe), 8 lanes
+        double *d = reinterpret_cast<double *>(lo);  // 8 doubles over lo[16]
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = fma(d[i], 1.0000001, 0.5);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = fma(d[i], 0.9999999, 0.25);
+      }
+    }
+  }
+  u32 acc = b;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc ^= lo[i] ^ hi[i];
+  if (acc == 0x12345u) sink[0] = acc;  // practically never true; keeps the chains live
+}
+
+namespace {
+thread_local char g_mb_err[256];
+}
+
+extern "C" int cuzk_imad_peak(int variant, int iters, double *ops_per_second_out) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return CUZK_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return CUZK_ERR_CUDA;
+  const int blocks = prop.multiProcessorCount * 8, threads = 256;
+  u32 *sink = nullptr;
+  if (cudaMalloc(&sink, 4) != cudaSuccess) return CUZK_ERR_CUDA;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0);
+    switch (variant) {
+      case 0: imad_peak_kernel<0><<<blocks, threads>>>(sink, iters, 1u + rep); break;
+      case 1: imad_peak_kernel<1><<<blocks, threads>>>(sink, iters, 1u + rep); break;
+      case 2: imad_peak_kernel<2><<<blocks, threads>>>(sink, iters, 1u + rep); break;
+      case 3: imad_peak_kernel<3><<<blocks, threads>>>(sink, iters, 1u + rep); break;
+      case 4: imad_peak_kernel<4><<<blocks, threads>>>(sink, iters, 1u + rep); break;
+      case 5: imad_peak_kernel<5><<<blocks, threads>>>(sink, iters, 1u + rep); break;
+      case 6: imad_peak_kernel<6><<<blocks, threads>>>(sink, iters, 1u + rep); break;
+      case 7: imad_peak_kernel<7><<<blocks, threads>>>(sink, iters, 1u + rep); break;
+      case 8: imad_peak_kernel<8><<<blocks, threads>>>(sink, iters, 1u + rep); break;
+      case 9: imad_peak_kernel<9><<<blocks, threads>>>(sink, iters, 1u + rep); break;
+      default: cudaFree(sink); return CUZK_ERR_INVALID;
+    }
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(sink); return CUZK_ERR_CUDA; }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  // counted operations per thread per trip (4 reps): variants 0-4, 8: 64; 5-7: 32 multiply-adds; 9: 64 DFMA
+  double per_trip = (variant >= 5 && variant <= 7) ? 32.0 : 64.0;
+  *ops_per_second_out = per_trip * (double)iters * (double)blocks * (double)threads / (best * 1e-3);
+  return CUZK_OK;
+}

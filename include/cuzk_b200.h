@@ -141,7 +141,8 @@ int cuzk_synth_u64_leaves(uint64_t *out, size_t n, uint64_t seed, uint64_t start
 
 /* integer-multiply pipe microbenchmark: runs `iters` rounds of dependent-free IMAD.WIDE chains on the whole
  * chip and returns measured 32x32->64 multiply-adds per second (the roofline denominator); variant selects
- * 0 = IMAD.WIDE.U32, 1 = IMAD (lo) 2 = IMAD.HI, 3 = IMAD.WIDE.U32.X carry chains, 4 = IADD3 */
+ * 0 = IMAD.WIDE.U32, 1 = IMAD (lo), 2 = IMAD.HI, 3 = IMAD.WIDE.U32.X carry chains, 4 = IADD3.X carry chains,
+ * 5/6/7 = IMAD.WIDE with 1/2/3 carry-chain adds per multiply (counts the multiplies), 8 = SEL, 9 = DFMA */
 int cuzk_imad_peak(int variant, int iters, double *ops_per_second_out);
 
 #ifdef __cplusplus
