@@ -158,6 +158,21 @@ __global__ void __launch_bounds__(kBlock) permutation_kernel(uint4 *states, size
   store_fr(states + 6 * i + 4, s2);
 }
 
+// test hook: one MDS layer on canonical states (mode 0 = production fast path with fallback, 1 = exact path only)
+__global__ void __launch_bounds__(kBlock) debug_mds_kernel(uint4 *states, size_t n, int mode) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u32 s0[8], s1[8], s2[8];
+  load_fr_plain(s0, states + 6 * i);
+  load_fr_plain(s1, states + 6 * i + 2);
+  load_fr_plain(s2, states + 6 * i + 4);
+  if (mode == 0) mds(s0, s1, s2);
+  else mds_exact(s0, s1, s2);
+  store_fr(states + 6 * i, s0);
+  store_fr(states + 6 * i + 2, s1);
+  store_fr(states + 6 * i + 4, s2);
+}
+
 // generic sponge: out[i] = sponge(in[i*width ..], ds)
 __global__ void __launch_bounds__(kBlock) sponge_kernel(const uint4 *__restrict__ in, int width, u32 ds_lo, u32 ds_hi,
                                                          uint4 *__restrict__ out, size_t n) {
@@ -584,6 +599,14 @@ int cuzk_poseidon_permutation(uint64_t *states, size_t n, int mem, void *stream)
   CK(cudaMemcpyAsync(states, d.p, n * 96, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return CUZK_OK;
+}
+
+int cuzk_debug_mds_layer(uint64_t *states, size_t n, int mode, void *stream) {
+  int rc = require_init();
+  if (rc) return rc;
+  if (n == 0) return CUZK_OK;
+  debug_mds_kernel<<<grid_for(n, kBlock), kBlock, 0, S(stream)>>>(reinterpret_cast<uint4 *>(states), n, mode);
+  return check_launch("debug_mds_kernel");
 }
 
 int cuzk_poseidon_sponge(const uint64_t *in, size_t width, uint64_t ds, uint64_t *out, size_t n, int mem, void *stream) {

@@ -271,7 +271,62 @@ __device__ __forceinline__ void fr_mul(u32 (&r)[8], const u32 (&a)[8], const u32
   fr_reduce_512(r, prod);
 }
 
-__device__ __forceinline__ void fr_sqr(u32 (&r)[8], const u32 (&a)[8]) { fr_mul(r, a, a); }
+// r[0..15] = a * a using the symmetry of the product: the 28 off-diagonal products are accumulated once
+// on the even/odd lanes, doubled, and the 8 diagonal squares are added by one carry-chained row
+// (36 IMAD.WIDE instead of 64).  Exact for any 256-bit a.
+__device__ __forceinline__ void sqr_wide_8(u32 (&r)[16], const u32 (&a)[8]) {
+  u32 e[16], o[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { e[i] = 0; o[i] = 0; }
+  // row i: a_i * a_j, j > i.  j - i odd -> odd position 2i+1+2t (accumulator o); j - i even -> even position (e).
+  // After row i every accumulator is < 2^(32(i+9)): the chain whose top lane ends at word i+8 has no carry out,
+  // the other one carries into word i+8 and stops there.
+  row_chain<4, 0>(o + 1, a + 1, a[0]);   // (0,1)(0,3)(0,5)(0,7): positions 1,3,5,7 -> words 1..8
+  row_chain<3, 0>(e + 2, a + 2, a[0]);   // (0,2)(0,4)(0,6): positions 2,4,6 -> words 2..7
+  e[8] = addc(e[8], 0u);
+  row_chain<3, 0>(o + 3, a + 2, a[1]);   // (1,2)(1,4)(1,6): positions 3,5,7 -> words 3..8
+  o[9] = addc(o[9], 0u);
+  row_chain<3, 0>(e + 4, a + 3, a[1]);   // (1,3)(1,5)(1,7): positions 4,6,8 -> words 4..9
+  row_chain<3, 0>(o + 5, a + 3, a[2]);   // (2,3)(2,5)(2,7): positions 5,7,9 -> words 5..10
+  row_chain<2, 0>(e + 6, a + 4, a[2]);   // (2,4)(2,6): positions 6,8 -> words 6..9
+  e[10] = addc(e[10], 0u);
+  row_chain<2, 0>(o + 7, a + 4, a[3]);   // (3,4)(3,6): positions 7,9 -> words 7..10
+  o[11] = addc(o[11], 0u);
+  row_chain<2, 0>(e + 8, a + 5, a[3]);   // (3,5)(3,7): positions 8,10 -> words 8..11
+  row_chain<2, 0>(o + 9, a + 5, a[4]);   // (4,5)(4,7): positions 9,11 -> words 9..12
+  row_chain<1, 0>(e + 10, a + 6, a[4]);  // (4,6): position 10 -> words 10,11
+  e[12] = addc(e[12], 0u);
+  row_chain<1, 0>(o + 11, a + 6, a[5]);  // (5,6): position 11 -> words 11,12
+  o[13] = addc(o[13], 0u);
+  row_chain<1, 0>(e + 12, a + 7, a[5]);  // (5,7): position 12 -> words 12,13
+  row_chain<1, 0>(o + 13, a + 7, a[6]);  // (6,7): position 13 -> words 13,14
+  // d = e + o (off-diagonal sum, < 2^511)
+  u32 d[16];
+  d[0] = 0;
+  d[1] = o[1];
+  d[2] = add_cc(e[2], o[2]);
+#pragma unroll
+  for (int i = 3; i < 15; ++i) d[i] = addc_cc(e[i], o[i]);
+  d[15] = addc(e[15], o[15]);
+  // doubled, then the diagonal a_i^2 at position 2i as one carry-chained row of eight lanes
+#pragma unroll
+  for (int i = 15; i >= 1; --i) r[i] = __funnelshift_l(d[i - 1], d[i], 1);
+  r[0] = 0;
+  r[0] = mad_lo_cc(a[0], a[0], r[0]);
+  r[1] = madc_hi_cc(a[0], a[0], r[1]);
+#pragma unroll
+  for (int i = 1; i < 8; ++i) {
+    r[2 * i] = madc_lo_cc(a[i], a[i], r[2 * i]);
+    r[2 * i + 1] = (i == 7) ? madc_hi(a[i], a[i], r[2 * i + 1]) : madc_hi_cc(a[i], a[i], r[2 * i + 1]);
+  }
+}
+
+// square : field_arithmetic.cpp:240-242 (= multiply(a, a), evaluated with the symmetric product)
+__device__ __forceinline__ void fr_sqr(u32 (&r)[8], const u32 (&a)[8]) {
+  u32 prod[16];
+  sqr_wide_8(prod, a);
+  fr_reduce_512(r, prod);
+}
 
 // power5 : field_arithmetic.cpp:332-338
 __device__ __forceinline__ void fr_pow5(u32 (&r)[8], const u32 (&a)[8]) {

@@ -19,6 +19,8 @@ constexpr int kPartial = 56;
 __constant__ u32 c_rc[kRounds * 3][2];
 
 // s += RC (RC < 2^64), s canonical on entry -> canonical on exit.  add_round_constants :128-134
+// The sum is < p + 2^64, so it can only reach p when its top word equals p's top word: the exact
+// compare-and-subtract runs on that (2^-30) branch only.
 __device__ __forceinline__ void arc_canon(u32 (&s)[8], int idx) {
   const u32 c0 = c_rc[idx][0], c1 = c_rc[idx][1];
   s[0] = add_cc(s[0], c0);
@@ -26,7 +28,7 @@ __device__ __forceinline__ void arc_canon(u32 (&s)[8], int idx) {
 #pragma unroll
   for (int i = 2; i < 7; ++i) s[i] = addc_cc(s[i], 0u);
   s[7] = addc(s[7], 0u);
-  cond_sub_mp<1>(s);
+  if (s[7] >= CUZK_P7) cond_sub_mp<1>(s);
 }
 
 // same for an arbitrary 256-bit s (first round of a caller-supplied state): wraps mod 2^256, full reduce
@@ -96,11 +98,115 @@ __device__ __forceinline__ void mds_row(u32 (&n)[8], const u32 (&s0)[8], const u
   fr_add_canon(n, b, a);
 }
 
-__device__ __forceinline__ void mds(u32 (&s0)[8], u32 (&s1)[8], u32 (&s2)[8]) {
+// exact MDS layer, term by term as the reference evaluates it (also the fallback of mds_fast)
+__device__ __noinline__ void mds_exact(u32 (&s0)[8], u32 (&s1)[8], u32 (&s2)[8]) {
   u32 n0[8], n1[8], n2[8];
   mds_row<7, 23, 8>(n0, s0, s1, s2);
   mds_row<26, 5, 4>(n1, s0, s1, s2);
   mds_row<15, 20, 9>(n2, s0, s1, s2);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s0[i] = n0[i]; s1[i] = n1[i]; s2[i] = n2[i]; }
+}
+
+// ---- fast MDS layer -----------------------------------------------------------------------------
+// With x = C*s = h*W + low (W = 2^256, h <= 4), the reference term is
+//     mul(C, s) = red(u),  u = (low + h*k) mod W = x - h*(W - k) - w*W,   w = [low + h*k >= W]
+// and W - k = 5p, so  u == x - w*k (mod p)  and the three-term row is
+//     n_i = (S_i - Wsum_i * k) mod p,   S_i = sum_j C_ij * s_j  (< 47p, nine words),  Wsum_i = sum_j w_ij.
+// S_i needs no carry handling (each 64-bit lane holds a sum < 2^39), the reduction is one quotient
+// estimate q^ in {q-1, q} from the top words, one multiply-add by (W - p), and one conditional subtract:
+//     y = S_i - Wsum_i*k - q^*p  ==  S_low + (q^ - 5*Wsum_i) * (W - p)   (mod W),   0 <= y < 2p.
+// The wrap bit w_ij = [low >= W - h*k] is decided from the top word of low; the two cases where the top
+// word cannot decide (carry into word 7 ambiguous, or low_7 equal to the threshold word; ~2^-27 per term)
+// set `unc` and the caller recomputes the layer with mds_exact.
+#define CUZK_NP0 (0u - CUZK_P0)
+#define CUZK_NP1 (~CUZK_P1)
+#define CUZK_NP2 (~CUZK_P2)
+#define CUZK_NP3 (~CUZK_P3)
+#define CUZK_NP4 (~CUZK_P4)
+#define CUZK_NP5 (~CUZK_P5)
+#define CUZK_NP6 (~CUZK_P6)
+#define CUZK_NP7 (~CUZK_P7)
+__host__ __device__ constexpr u32 np_limb(int i) {   // limbs of W - p (P0 != 0, so no borrow past limb 0)
+  const u32 v[8] = {CUZK_NP0, CUZK_NP1, CUZK_NP2, CUZK_NP3, CUZK_NP4, CUZK_NP5, CUZK_NP6, CUZK_NP7};
+  return v[i];
+}
+constexpr u32 kQuotMagic = (u32)((1ull << 61) / (u64)(CUZK_P7 + 1u));   // floor(2^61 / (p_top + 1))
+
+// wrap bit of one term: adds w to wsum, ORs the "cannot decide" conditions into unc
+template <u32 C>
+__device__ __forceinline__ void mds_wrap_bit(u32 &wsum, u32 &unc, const u32 (&s)[8]) {
+  const u64 y = (u64)s[6] * C;                       // word 6 product: its high half carries into word 7
+  const u64 z = (u64)s[7] * C + (y >> 32);           // (h : low_7) unless the carry out of word 6 is ambiguous
+  const u32 h = (u32)(z >> 32), low7 = (u32)z;
+  unc |= ((u32)y >= 0xFFFFFFE0u) ? 1u : 0u;          // lower words could still push a carry into word 7
+  const u32 fl = h * CUZK_K7 + ((h * 5u) >> 3);      // floor(h*k / 2^224) for h = 0..4
+  const u32 t = add_cc(low7, fl);                    // low_7 > 0xFFFFFFFF - fl  <=>  carry out
+  wsum = addc(wsum, 0u);
+  unc |= (t == 0xFFFFFFFFu) ? 1u : 0u;               // low_7 equals the threshold word: lower words decide
+}
+
+template <u32 C0, u32 C1, u32 C2>
+__device__ __forceinline__ void mds_row_fast(u32 (&n)[8], u32 &unc, const u32 (&s0)[8], const u32 (&s1)[8], const u32 (&s2)[8]) {
+  u32 wsum = 0;
+  mds_wrap_bit<C0>(wsum, unc, s0);
+  mds_wrap_bit<C1>(wsum, unc, s1);
+  mds_wrap_bit<C2>(wsum, unc, s2);
+  // S = sum_j C_j * s_j on even/odd lanes (no carries: every lane < 3 * 26 * 2^32)
+  u64 e[4], o[4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    e[m] = (u64)s0[2 * m] * C0 + (u64)s1[2 * m] * C1 + (u64)s2[2 * m] * C2;
+    o[m] = (u64)s0[2 * m + 1] * C0 + (u64)s1[2 * m + 1] * C1 + (u64)s2[2 * m + 1] * C2;
+  }
+  u32 S[9];
+  S[0] = (u32)e[0];
+  S[1] = add_cc((u32)(e[0] >> 32), (u32)o[0]);
+  S[2] = addc_cc((u32)e[1], (u32)(o[0] >> 32));
+  S[3] = addc_cc((u32)(e[1] >> 32), (u32)o[1]);
+  S[4] = addc_cc((u32)e[2], (u32)(o[1] >> 32));
+  S[5] = addc_cc((u32)(e[2] >> 32), (u32)o[2]);
+  S[6] = addc_cc((u32)e[3], (u32)(o[2] >> 32));
+  S[7] = addc_cc((u32)(e[3] >> 32), (u32)o[3]);
+  S[8] = addc(0u, (u32)(o[3] >> 32));
+  // quotient estimate: L' <= floor((S - wsum*k) / 2^228), q^ = floor(L' * floor(2^61/(p7+1)) / 2^57)
+  const u32 a4 = (S[8] << 28) | (S[7] >> 4);
+  const u32 lp = a4 - ((wsum * (CUZK_K7 + 1u) + 15u) >> 4);
+  const u32 qhat = __umulhi(lp, kQuotMagic) >> 25;
+  const u32 q = qhat - 5u * wsum;                    // >= 0: every wrap puts >= 1.89 W into S - wsum*k
+  // y = S_low + q * (W - p)  (mod W)
+  u32 ye[8], yo[9];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ye[i] = S[i];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) yo[i] = 0;
+  ye[0] = mad_lo_cc(q, np_limb(0), ye[0]);
+  ye[1] = madc_hi_cc(q, np_limb(0), ye[1]);
+#pragma unroll
+  for (int m = 1; m < 4; ++m) {
+    ye[2 * m] = madc_lo_cc(q, np_limb(2 * m), ye[2 * m]);
+    ye[2 * m + 1] = madc_hi_cc(q, np_limb(2 * m), ye[2 * m + 1]);
+  }
+#pragma unroll
+  for (int m = 0; m < 4; ++m) mad_wide(yo[2 * m + 1], yo[2 * m + 2], q, np_limb(2 * m + 1));
+  n[0] = ye[0];
+  n[1] = add_cc(ye[1], yo[1]);
+#pragma unroll
+  for (int i = 2; i < 7; ++i) n[i] = addc_cc(ye[i], yo[i]);
+  n[7] = addc(ye[7], yo[7]);
+  cond_sub_mp<1>(n);
+}
+
+__device__ __forceinline__ void mds(u32 (&s0)[8], u32 (&s1)[8], u32 (&s2)[8]) {
+  u32 n0[8], n1[8], n2[8];
+  u32 unc = 0;
+  mds_row_fast<7, 23, 8>(n0, unc, s0, s1, s2);
+  mds_row_fast<26, 5, 4>(n1, unc, s0, s1, s2);
+  mds_row_fast<15, 20, 9>(n2, unc, s0, s1, s2);
+  if (unc != 0) {   // ~2^-24 per layer: recompute exactly, term by term
+    mds_exact(s0, s1, s2);
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s0[i] = n0[i]; s1[i] = n1[i]; s2[i] = n2[i]; }
 }

@@ -139,6 +139,10 @@ int cuzk_merkle_verify_batch(const uint64_t *leaf_values, const uint64_t *siblin
 int cuzk_synth_elements(uint64_t *out, size_t n, uint64_t seed, uint64_t start, int canonical, void *stream);
 int cuzk_synth_u64_leaves(uint64_t *out, size_t n, uint64_t seed, uint64_t start, void *stream);
 
+/* test hook (device pointers): applies ONE MDS layer (apply_mds_matrix, poseidon.cpp:148-167) in place to n
+ * canonical 3-element states; mode 0 = the production fast path with its exact fallback, 1 = exact path only */
+int cuzk_debug_mds_layer(uint64_t *states, size_t n, int mode, void *stream);
+
 /* integer-multiply pipe microbenchmark: runs `iters` rounds of dependent-free IMAD.WIDE chains on the whole
  * chip and returns measured 32x32->64 multiply-adds per second (the roofline denominator); variant selects
  * 0 = IMAD.WIDE.U32, 1 = IMAD (lo), 2 = IMAD.HI, 3 = IMAD.WIDE.U32.X carry chains, 4 = IADD3.X carry chains,

@@ -216,6 +216,24 @@ void cuzk_oracle_permutation(uint64_t *state) {
   }
 }
 
+/* one apply_mds_matrix (poseidon.cpp:148-167) on n states, in place -- used to test the GPU MDS layer alone */
+void cuzk_oracle_batch_mds_layer(uint64_t *states, size_t n) {
+  pthread_once(&g_once, constants_init);
+  for (size_t k = 0; k < n; ++k) {
+    uint64_t(*s)[4] = (uint64_t(*)[4])(states + 12 * k);
+    uint64_t nn[T][4];
+    for (int i = 0; i < T; ++i) {
+      memset(nn[i], 0, sizeof nn[i]);
+      for (int j = 0; j < T; ++j) {
+        uint64_t tmp[4];
+        cuzk_oracle_fr_mul(g_mds[i * T + j], s[j], tmp);
+        cuzk_oracle_fr_add(nn[i], tmp, nn[i]);
+      }
+    }
+    memcpy(s, nn, sizeof nn);
+  }
+}
+
 /* sponge : poseidon.cpp:103-126.  domain separator is a full element. */
 void cuzk_oracle_sponge(const uint64_t *inputs, size_t n, const uint64_t ds[4], uint64_t out[4]) {
   uint64_t st[T][4];

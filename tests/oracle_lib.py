@@ -373,3 +373,13 @@ def synth_u64_leaves(seed: int, n: int, start: int = 0) -> np.ndarray:
     a = np.zeros((n, 4), dtype=np.uint64)
     a[:, 0] = splitmix64(seed, np.arange(start, start + n, dtype=np.uint64))
     return a
+
+
+def oracle_mds_layer(oracle: "Oracle", states: np.ndarray) -> np.ndarray:
+    """One MDS layer (apply_mds_matrix) on (n, 3, 4) states via the oracle."""
+    s = np.array(states, dtype=np.uint64).reshape(-1, 3, 4).copy()
+    f = oracle.lib.cuzk_oracle_batch_mds_layer
+    f.argtypes = [_u64p, C.c_size_t]
+    f.restype = None
+    f(_p(s), s.shape[0])
+    return s

@@ -271,3 +271,24 @@ def test_subtree_roots_and_top_equal_full_build(gpu, oracle):
         real = -(-n // span)
         if real < count:
             assert (to_host(roots[real:]) == gpu.padding_root(arity, height)).all()
+
+
+def test_mds_layer_fast_path_and_fallback(gpu, oracle):
+    """The fast MDS layer (linear form + wrap count + exact fallback) against the oracle's term-by-term layer, on
+    states crafted to sit on every decision boundary, and against the GPU's own exact path."""
+    import torch
+
+    from cuzk_b200 import lib
+    from oracle_lib import oracle_mds_layer
+    from test_oracle import craft_mds_states
+
+    L = lib.get_lib()
+    rng = np.random.default_rng(99)
+    st = np.concatenate([craft_mds_states(rng), rnd(rng, 3 * 200_000, True).reshape(-1, 3, 4)])
+    want = oracle_mds_layer(oracle, st)
+    for mode in (0, 1):
+        d = to_dev(st.reshape(-1, 4))
+        L.check(L.cuzk_debug_mds_layer(d.data_ptr(), st.shape[0], mode, None), "debug_mds")
+        got = to_host(d).reshape(-1, 3, 4)
+        bad = np.nonzero((got != want).any(axis=(1, 2)))[0]
+        assert bad.size == 0, (mode, bad[:4], hexes(st[bad[0]]) if bad.size else None)

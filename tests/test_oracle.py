@@ -201,3 +201,51 @@ def test_multiply_is_not_modular(oracle):
         return red((low + hc) % W)
 
     assert got == [model(x, y) for x, y in zip(array_to_ints(a), array_to_ints(b))]
+
+
+def craft_mds_states(rng):
+    """Canonical states that hit every special case of the GPU's fast MDS layer (cuzk_b200/csrc/poseidon.cuh):
+    wrap thresholds of every (constant, h), ambiguous carries into word 7, tiny and maximal values."""
+    from oracle_lib import K_INT, P_INT
+
+    W = 1 << 256
+    vals = [0, 1, 2, P_INT - 1, P_INT - 2, P_INT // 2]
+    for c in (7, 23, 8, 26, 5, 4, 15, 20, 9):
+        for h in range(1, 5):
+            T = (h + 1) * W - h * K_INT  # c*s >= T  <=>  the term wraps
+            for d in range(-3, 4):
+                vals.append((T + d * c + c - 1) // c)          # around the exact threshold
+                vals.append(((h + 1) * W + d * c) // c)         # around the next multiple of W
+            top = ((h << 32) | (0xFFFFFFFF - ((h * K_INT) >> 224))) << 224   # low_7 == threshold word, lower words vary
+            for lowbits in (0, 1, (1 << 224) - 1, (1 << 223), int(rng.integers(0, 2**62)) << 160):
+                vals.append((top + lowbits) // c)
+        a2 = (c & -c).bit_length() - 1                                      # c = 2^a2 * odd
+        inv = pow(c >> a2, -1, 1 << 32)
+        for tgt in (0xFFFFFFE0, 0xFFFFFFF5, 0xFFFFFFFF, 0xFFFFFFDF):       # lo32(c * s_6) at the ambiguity limit
+            s6 = (((tgt >> a2) * inv) & 0xFFFFFFFF) % (1 << (32 - a2))     # c * s6 = tgt rounded down to 2^a2 (mod 2^32)
+            assert (c * s6) & 0xFFFFFFFF == (tgt >> a2) << a2
+            for s7 in (0, 0x10000000, 0x30644E72, 0x2FFFFFFF):
+                for low in (0, (1 << 192) - 1, int(rng.integers(0, 2**62)) << 128):
+                    vals.append((s7 << 224) | (s6 << 192) | low)
+    vals = [v for v in vals if 0 <= v < P_INT]
+    picks = rng.integers(0, len(vals), size=(6000, 3))
+    states = np.stack([ints_to_array([vals[i] for i in picks[:, j]]) for j in range(3)], axis=1)
+    rand = rnd(rng, 3 * 3000, True).reshape(-1, 3, 4)
+    rand[::3, 1] = ints_to_array([vals[i] for i in rng.integers(0, len(vals), size=len(rand[::3]))])
+    return np.concatenate([states, rand])
+
+
+def test_oracle_mds_layer_vs_reference_ops(oracle, ref):
+    """The oracle's single MDS layer equals the composition of the reference's multiply/add (poseidon.cpp:148-167)."""
+    from oracle_lib import oracle_mds_layer
+
+    rng = np.random.default_rng(77)
+    st = craft_mds_states(rng)[:3000]
+    got = oracle_mds_layer(oracle, st)
+    mds = ref.mds()
+    for i in range(3):
+        acc = np.zeros((st.shape[0], 4), dtype=np.uint64)
+        for j in range(3):
+            term = ref.batch_fr("mul", np.tile(mds[3 * i + j], (st.shape[0], 1)), st[:, j])
+            acc = ref.batch_fr("add", acc, term)
+        assert (got[:, i] == acc).all(), i
