@@ -65,7 +65,13 @@ inline unsigned grid_for(size_t n, unsigned block) {
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-constexpr int kBlock = 128;
+#ifndef CUZK_BLOCK
+#define CUZK_BLOCK 128
+#endif
+#ifndef CUZK_MIN_BLOCKS
+#define CUZK_MIN_BLOCKS 7   // 72 registers: measured best on B200 (profiles/r01_tuning_notes.md)
+#endif
+constexpr int kBlock = CUZK_BLOCK;
 
 // generate_round_constants : poseidon.cpp:33-44, evaluated with the reference's own multiply/add
 __global__ void gen_round_constants_kernel(uint4 *out) {
@@ -114,7 +120,7 @@ __global__ void __launch_bounds__(kBlock) fr_batch_kernel(const uint4 *__restric
 }
 
 // batch_hash_single: state [1, in, 0]
-__global__ void __launch_bounds__(kBlock) hash_single_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, size_t n) {
+__global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) hash_single_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   u32 s0[8], s1[8], s2[8], x[8];
@@ -128,7 +134,7 @@ __global__ void __launch_bounds__(kBlock) hash_single_kernel(const uint4 *__rest
 }
 
 // batch_hash_pairs: state [2, l, r]  -- the headline kernel
-__global__ void __launch_bounds__(kBlock) hash_pairs_kernel(const uint4 *__restrict__ l, const uint4 *__restrict__ r,
+__global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) hash_pairs_kernel(const uint4 *__restrict__ l, const uint4 *__restrict__ r,
                                                              uint4 *__restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -145,7 +151,7 @@ __global__ void __launch_bounds__(kBlock) hash_pairs_kernel(const uint4 *__restr
 }
 
 // batch_permutation: in-place, caller-supplied (possibly non-canonical) states
-__global__ void __launch_bounds__(kBlock) permutation_kernel(uint4 *states, size_t n) {
+__global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) permutation_kernel(uint4 *states, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   u32 s0[8], s1[8], s2[8];
@@ -174,7 +180,7 @@ __global__ void __launch_bounds__(kBlock) debug_mds_kernel(uint4 *states, size_t
 }
 
 // generic sponge: out[i] = sponge(in[i*width ..], ds)
-__global__ void __launch_bounds__(kBlock) sponge_kernel(const uint4 *__restrict__ in, int width, u32 ds_lo, u32 ds_hi,
+__global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) sponge_kernel(const uint4 *__restrict__ in, int width, u32 ds_lo, u32 ds_hi,
                                                          uint4 *__restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -226,22 +232,81 @@ __global__ void merkle_pad_leaves_kernel(const uint4 *__restrict__ leaves, size_
   out[2 * i + 1] = src[1];
 }
 
-// one level: out[i] = hash_multiple(in[i*arity .. i*arity+arity-1]) for the `real` nodes that cover at
-// least one real leaf; the remaining out_count - real nodes are the padding constant of this level.
+// one level: out[i] = hash_multiple(in[i*arity .. i*arity+arity-1]).  Only the first `in_real` inputs exist in
+// memory; children beyond them are the padding constant of the input level (pad_in), and output nodes with no real
+// child are the padding constant of the output level (pad_out) -- never hashed.
 // build_level_kernel : merkle_tree_cuda.cu:45-64 / build_tree_bottom_up : merkle_tree.cpp:66-97
-__global__ void __launch_bounds__(kBlock) merkle_level_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out,
-                                                               size_t real, size_t out_count, int arity,
-                                                               const uint4 *__restrict__ pad_const) {
+__global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) merkle_level_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out,
+                                                               size_t in_real, size_t out_count, int arity,
+                                                               const uint4 *__restrict__ pad_in, const uint4 *__restrict__ pad_out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= out_count) return;
-  if (i >= real) {
-    out[2 * i] = pad_const[0];
-    out[2 * i + 1] = pad_const[1];
+  const size_t first = i * (size_t)arity;
+  if (first >= in_real) {
+    out[2 * i] = pad_out[0];
+    out[2 * i + 1] = pad_out[1];
     return;
   }
-  const uint4 *base = in + 2 * i * (size_t)arity;
   u32 r[8];
-  sponge_n(r, 3u, arity, [&](u32(&x)[8], int j) { load_fr_plain(x, base + 2 * j); });
+  sponge_n(r, 3u, arity, [&](u32(&x)[8], int j) {
+    const uint4 *src = (first + j < in_real) ? in + 2 * (first + j) : pad_in;
+    load_fr_plain(x, src);
+  });
+  store_fr(out + 2 * i, r);
+}
+
+// two fused levels: thread i hashes `arity` groups of `arity` inputs into its own shared-memory slots and then hashes
+// those into out[i]; the middle level never reaches HBM unless `mid_out` is given (full-tree builds keep every level).
+// Same padding rules as merkle_level_kernel (pad_in / pad_mid / pad_out are consecutive padding constants).
+__global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) merkle_fused2_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ mid_out,
+                                                                uint4 *__restrict__ out, size_t in_real, size_t out_count,
+                                                                int arity, const uint4 *__restrict__ pad) {
+  extern __shared__ uint4 smem[];                    // [2 * arity][kBlock] uint4: slot-major, so a warp's accesses never conflict
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= out_count) return;
+  const uint4 *pad_in = pad, *pad_mid = pad + 2, *pad_out = pad + 4;
+  const size_t span = (size_t)arity * arity;
+  if (i * span >= in_real) {
+    out[2 * i] = pad_out[0];
+    out[2 * i + 1] = pad_out[1];
+    if (mid_out) {
+      for (int g = 0; g < arity; ++g) {
+        mid_out[2 * (i * arity + g)] = pad_mid[0];
+        mid_out[2 * (i * arity + g) + 1] = pad_mid[1];
+      }
+    }
+    return;
+  }
+  uint4 *mine = smem + threadIdx.x;                  // slot s of this thread lives at mine[s * kBlock]
+#pragma unroll 1
+  for (int g = 0; g < arity; ++g) {
+    const size_t first = i * span + (size_t)g * arity;
+    uint4 lo, hi;
+    if (first >= in_real) {
+      lo = pad_mid[0];
+      hi = pad_mid[1];
+    } else {
+      u32 r[8];
+      sponge_n(r, 3u, arity, [&](u32(&x)[8], int j) {
+        const uint4 *src = (first + j < in_real) ? in + 2 * (first + j) : pad_in;
+        load_fr_plain(x, src);
+      });
+      lo = make_uint4(r[0], r[1], r[2], r[3]);
+      hi = make_uint4(r[4], r[5], r[6], r[7]);
+    }
+    mine[(2 * g) * kBlock] = lo;
+    mine[(2 * g + 1) * kBlock] = hi;
+    if (mid_out) {
+      mid_out[2 * (i * arity + g)] = lo;
+      mid_out[2 * (i * arity + g) + 1] = hi;
+    }
+  }
+  u32 r[8];
+  sponge_n(r, 3u, arity, [&](u32(&x)[8], int j) {
+    const uint4 a = mine[(2 * j) * kBlock], b = mine[(2 * j + 1) * kBlock];
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
+    x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+  });
   store_fr(out + 2 * i, r);
 }
 
@@ -278,7 +343,7 @@ __global__ void merkle_prove_kernel(const uint4 *__restrict__ levels, size_t n, 
 }
 
 // verify: one thread per proof.  batch_verify_proofs_kernel : merkle_tree_cuda.cu:67-118 / verify_proof : merkle_tree.cpp:214-254
-__global__ void __launch_bounds__(kBlock) merkle_verify_kernel(const uint4 *__restrict__ leaves, const uint4 *__restrict__ sib,
+__global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) merkle_verify_kernel(const uint4 *__restrict__ leaves, const uint4 *__restrict__ sib,
                                                                 const u32 *__restrict__ pos, int nlv, int arity,
                                                                 const uint4 *__restrict__ root, uint8_t *__restrict__ results,
                                                                 size_t num_proofs) {
@@ -343,14 +408,66 @@ __global__ void synth_u64_leaves_kernel(u64 *out, size_t n, u64 seed, u64 start)
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-struct DevBuf {
-  void *p = nullptr;
-  ~DevBuf() {
-    if (p) cudaFree(p);
+// Host-buffer calls (mem == CUZK_MEM_HOST) stage through library-owned device buffers that are kept between calls
+// (the reference mallocs and frees on every call, poseidon_cuda.cu:374-408) and are cut into chunks that alternate
+// between two internal streams, so the H2D copy of chunk c+1 and the D2H copy of chunk c-1 overlap the kernel of chunk c.
+constexpr int kPipeStreams = 2;
+constexpr int kPipeSlots = 4;                       // up to 3 inputs + 1 output per stream
+constexpr size_t kHashChunk = 148 * 7 * 128;        // one resident wave of one-thread-per-hash CTAs
+constexpr size_t kCheapChunk = 1 << 20;             // element-wise field ops
+constexpr int kWsSlots = 6;
+
+struct HostPath {
+  cudaStream_t stream[kPipeStreams] = {nullptr, nullptr};
+  void *buf[kPipeStreams][kPipeSlots] = {};
+  size_t cap[kPipeStreams][kPipeSlots] = {};
+  void *ws[kWsSlots] = {};
+  size_t ws_cap[kWsSlots] = {};
+  bool ready = false;
+} g_hp;
+std::mutex g_hp_mu;   // host-buffer calls serialise on the staging buffers
+
+int hp_reserve(void *&p, size_t &cap, size_t bytes) {
+  if (bytes <= cap) return CUZK_OK;
+  if (p) {
+    CK(cudaDeviceSynchronize());
+    CK(cudaFree(p));
+    p = nullptr;
+    cap = 0;
   }
-  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
-  template <class T> T *as() { return reinterpret_cast<T *>(p); }
-};
+  size_t want = bytes + bytes / 4;
+  CK(cudaMalloc(&p, want));
+  cap = want;
+  return CUZK_OK;
+}
+int ws_get(int slot, size_t bytes, void **out) {
+  int rc = hp_reserve(g_hp.ws[slot], g_hp.ws_cap[slot], bytes ? bytes : 1);
+  *out = g_hp.ws[slot];
+  return rc;
+}
+int hp_start() {
+  if (g_hp.ready) return CUZK_OK;
+  for (int i = 0; i < kPipeStreams; ++i) CK(cudaStreamCreateWithFlags(&g_hp.stream[i], cudaStreamNonBlocking));
+  g_hp.ready = true;
+  return CUZK_OK;
+}
+void hp_stop() {
+  for (int i = 0; i < kPipeStreams; ++i) {
+    for (int j = 0; j < kPipeSlots; ++j) {
+      if (g_hp.buf[i][j]) cudaFree(g_hp.buf[i][j]);
+      g_hp.buf[i][j] = nullptr;
+      g_hp.cap[i][j] = 0;
+    }
+    if (g_hp.stream[i]) cudaStreamDestroy(g_hp.stream[i]);
+    g_hp.stream[i] = nullptr;
+  }
+  for (int j = 0; j < kWsSlots; ++j) {
+    if (g_hp.ws[j]) cudaFree(g_hp.ws[j]);
+    g_hp.ws[j] = nullptr;
+    g_hp.ws_cap[j] = 0;
+  }
+  g_hp.ready = false;
+}
 
 int require_init() {
   if (g_refcount <= 0) return fail(CUZK_ERR_CUDA, "cuzk_b200: library not initialised (call cuzk_init)");
@@ -361,6 +478,40 @@ int check_launch(const char *what) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, what);
+  return CUZK_OK;
+}
+
+// Chunked, double-buffered host->device->host pass.  `nin` input arrays of `in_bytes[k]` bytes per unit, one output
+// array of `out_bytes` per unit (out may alias in[0] for in-place ops).  launch(stream, d_in[], d_out, m) enqueues the
+// kernel(s) for m units.  Returns after every result byte is in `out`.
+template <class Launch>
+int host_pipeline(size_t n, size_t chunk, int nin, const void *const *in, const size_t *in_bytes, void *out, size_t out_bytes,
+                  bool out_aliases_in0, Launch launch) {
+  std::lock_guard<std::mutex> lk(g_hp_mu);
+  int rc = hp_start();
+  if (rc) return rc;
+  if (chunk > n) chunk = n;
+  for (int s = 0; s < kPipeStreams; ++s) {
+    for (int k = 0; k < nin; ++k)
+      if ((rc = hp_reserve(g_hp.buf[s][k], g_hp.cap[s][k], chunk * in_bytes[k]))) return rc;
+    if (!out_aliases_in0 && (rc = hp_reserve(g_hp.buf[s][kPipeSlots - 1], g_hp.cap[s][kPipeSlots - 1], chunk * out_bytes))) return rc;
+  }
+  size_t done = 0;
+  for (int c = 0; done < n; ++c) {
+    const int s = c % kPipeStreams;
+    const size_t m = (n - done < chunk) ? n - done : chunk;
+    cudaStream_t st = g_hp.stream[s];
+    void *d_in[kPipeSlots] = {};
+    for (int k = 0; k < nin; ++k) {
+      d_in[k] = g_hp.buf[s][k];
+      CK(cudaMemcpyAsync(d_in[k], static_cast<const char *>(in[k]) + done * in_bytes[k], m * in_bytes[k], cudaMemcpyHostToDevice, st));
+    }
+    void *d_out = out_aliases_in0 ? d_in[0] : g_hp.buf[s][kPipeSlots - 1];
+    if ((rc = launch(st, d_in, d_out, m))) return rc;
+    CK(cudaMemcpyAsync(static_cast<char *>(out) + done * out_bytes, d_out, m * out_bytes, cudaMemcpyDeviceToHost, st));
+    done += m;
+  }
+  for (int s = 0; s < kPipeStreams; ++s) CK(cudaStreamSynchronize(g_hp.stream[s]));
   return CUZK_OK;
 }
 
@@ -385,6 +536,8 @@ int check_arity(unsigned arity) {
   return CUZK_OK;
 }
 
+inline size_t ceil_div(size_t a, size_t b) { return (a + b - 1) / b; }
+
 // device-pointer implementations ------------------------------------------------------------------
 int fr_batch_dev(int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n, cudaStream_t st) {
   if (n == 0) return CUZK_OK;
@@ -402,30 +555,100 @@ int fr_batch_dev(int op, const uint64_t *a, const uint64_t *b, uint64_t *out, si
   return check_launch("fr_batch_kernel");
 }
 
+// Two levels are fused per launch while the upper of the two still fills the chip; narrower levels run one launch
+// per level so that each node keeps its own thread (a fused thread hashes arity + 1 nodes back to back).
+constexpr size_t kFuseMinOut = 148 * 7 * 128;
+
+int launch_level(const uint4 *in, uint4 *out, size_t in_real, size_t out_count, unsigned arity, const uint4 *pad_in, cudaStream_t st) {
+  merkle_level_kernel<<<grid_for(out_count, kBlock), kBlock, 0, st>>>(in, out, in_real, out_count, (int)arity, pad_in, pad_in + 2);
+  return check_launch("merkle_level_kernel");
+}
+int launch_fused2(const uint4 *in, uint4 *mid, uint4 *out, size_t in_real, size_t out_count, unsigned arity, const uint4 *pad_in,
+                  cudaStream_t st) {
+  const size_t smem = (size_t)2 * arity * kBlock * sizeof(uint4);
+  merkle_fused2_kernel<<<grid_for(out_count, kBlock), kBlock, smem, st>>>(in, mid, out, in_real, out_count, (int)arity, pad_in);
+  return check_launch("merkle_fused2_kernel");
+}
+
 int merkle_build_dev(const uint64_t *leaves, size_t n, unsigned arity, uint64_t *levels_out, cudaStream_t st) {
   int rc = ensure_padding(arity);
   if (rc) return rc;
   const uint4 *pad = reinterpret_cast<const uint4 *>(g_d_pad[arity]);
   size_t padded = cuzk_merkle_padded_leaves(n, arity);
-  uint4 *lv = reinterpret_cast<uint4 *>(levels_out);
-  merkle_pad_leaves_kernel<<<grid_for(padded, 256), 256, 0, st>>>(reinterpret_cast<const uint4 *>(leaves), n, padded, pad, lv);
-  rc = check_launch("merkle_pad_leaves_kernel");
-  if (rc) return rc;
+  if ((int)cuzk_merkle_num_levels(n, arity) >= g_pad_levels[arity]) return fail(CUZK_ERR_INVALID, "tree too tall");
+  uint4 *cur = reinterpret_cast<uint4 *>(levels_out);
+  merkle_pad_leaves_kernel<<<grid_for(padded, 256), 256, 0, st>>>(reinterpret_cast<const uint4 *>(leaves), n, padded, pad, cur);
+  if ((rc = check_launch("merkle_pad_leaves_kernel"))) return rc;
   size_t p = padded, real = n;
   int level = 0;
-  uint4 *cur = lv;
   while (p > 1) {
-    uint4 *nxt = cur + 2 * p;
-    size_t q = p / arity;
-    real = (real + arity - 1) / arity;
-    ++level;
-    if (level >= g_pad_levels[arity]) return fail(CUZK_ERR_INVALID, "tree too tall");
-    merkle_level_kernel<<<grid_for(q, kBlock), kBlock, 0, st>>>(cur, nxt, real, q, (int)arity, pad + 2 * level);
-    rc = check_launch("merkle_level_kernel");
-    if (rc) return rc;
-    cur = nxt;
-    p = q;
+    const size_t q = p / arity;
+    if (q > 1 && q / arity >= kFuseMinOut) {
+      const size_t q2 = q / arity;
+      if ((rc = launch_fused2(cur, cur + 2 * p, cur + 2 * p + 2 * q, real, q2, arity, pad + 2 * level, st))) return rc;
+      cur += 2 * p + 2 * q;
+      real = ceil_div(ceil_div(real, arity), arity);
+      p = q2;
+      level += 2;
+    } else {
+      if ((rc = launch_level(cur, cur + 2 * p, real, q, arity, pad + 2 * level, st))) return rc;
+      cur += 2 * p;
+      real = ceil_div(real, arity);
+      p = q;
+      level += 1;
+    }
   }
+  return CUZK_OK;
+}
+
+// roots of `count` consecutive subtrees of arity^height (virtual) leaves whose first n leaves are in memory
+int subtree_roots_dev(const uint64_t *leaves, size_t n, unsigned arity, unsigned height, size_t count, uint64_t *roots_out,
+                      cudaStream_t st) {
+  int rc = ensure_padding(arity);
+  if (rc) return rc;
+  if ((int)height + 1 >= g_pad_levels[arity]) return fail(CUZK_ERR_INVALID, "subtree too tall");
+  const uint4 *pad = reinterpret_cast<const uint4 *>(g_d_pad[arity]);
+  if (height == 0) {
+    merkle_pad_leaves_kernel<<<grid_for(count, 256), 256, 0, st>>>(reinterpret_cast<const uint4 *>(leaves), n, count, pad,
+                                                                  reinterpret_cast<uint4 *>(roots_out));
+    return check_launch("merkle_pad_leaves_kernel");
+  }
+  // stream-ordered scratch for the levels between the leaves and the roots; only nodes with a real leaf below them are stored
+  void *scratch[2] = {nullptr, nullptr};
+  auto release = [&]() {
+    for (void *s : scratch)
+      if (s) cudaFreeAsync(s, st);
+  };
+  const uint4 *cur = reinterpret_cast<const uint4 *>(leaves);
+  size_t real = n;
+  unsigned level = 0;
+  int flip = 0;
+  while (level < height) {
+    const unsigned step = (height - level >= 2 && ceil_div(real, (size_t)arity * arity) >= kFuseMinOut) ? 2 : 1;
+    const bool last = level + step == height;
+    size_t out_real = ceil_div(real, arity);
+    if (step == 2) out_real = ceil_div(out_real, arity);
+    const size_t out_count = last ? count : out_real;
+    uint4 *dst;
+    if (last) {
+      dst = reinterpret_cast<uint4 *>(roots_out);
+    } else {
+      if (scratch[flip]) { cudaFreeAsync(scratch[flip], st); scratch[flip] = nullptr; }
+      cudaError_t e = cudaMallocAsync(&scratch[flip], (out_count ? out_count : 1) * 32, st);
+      if (e != cudaSuccess) { release(); return cuda_fail(e, "cudaMallocAsync(scratch)"); }
+      dst = reinterpret_cast<uint4 *>(scratch[flip]);
+      flip ^= 1;
+    }
+    if (out_count) {
+      rc = (step == 2) ? launch_fused2(cur, nullptr, dst, real, out_count, arity, pad + 2 * level, st)
+                       : launch_level(cur, dst, real, out_count, arity, pad + 2 * level, st);
+      if (rc) { release(); return rc; }
+    }
+    cur = dst;
+    real = out_real;
+    level += step;
+  }
+  release();
   return CUZK_OK;
 }
 
@@ -437,7 +660,7 @@ int merkle_build_dev(const uint64_t *leaves, size_t n, unsigned arity, uint64_t 
 extern "C" {
 
 const char *cuzk_last_error(void) { return g_err.c_str(); }
-const char *cuzk_version(void) { return "cuzk_b200 0.1 (sm_100a)"; }
+const char *cuzk_version(void) { return "cuzk_b200 0.2 (sm_100a)"; }
 uint64_t cuzk_launch_count(void) { return g_launches.load(); }
 
 int cuzk_device_count(void) {
@@ -464,13 +687,21 @@ int cuzk_init(int device) {
   CK(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10) return fail(CUZK_ERR_CUDA, "cuzk_init: sm_100a (Blackwell B200) device required");
   g_sm_count = prop.multiProcessorCount;
+  // keep stream-ordered scratch in the pool between calls
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
   // round constants: generate on the device with the reference formula, check the <2^64 fast-path assumption
-  DevBuf d;
-  CK(d.alloc(sizeof g_host_rc));
-  gen_round_constants_kernel<<<2, 96>>>(d.as<uint4>());
+  void *d = nullptr;
+  CK(cudaMalloc(&d, sizeof g_host_rc));
+  gen_round_constants_kernel<<<2, 96>>>(reinterpret_cast<uint4 *>(d));
   int rc = check_launch("gen_round_constants_kernel");
-  if (rc) return rc;
-  CK(cudaMemcpy(g_host_rc, d.p, sizeof g_host_rc, cudaMemcpyDeviceToHost));
+  if (rc) { cudaFree(d); return rc; }
+  e = cudaMemcpy(g_host_rc, d, sizeof g_host_rc, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(round constants)");
   u32 packed[kRounds * 3][2];
   for (int i = 0; i < kRounds * 3; ++i) {
     if (g_host_rc[4 * i + 1] | g_host_rc[4 * i + 2] | g_host_rc[4 * i + 3])
@@ -491,10 +722,15 @@ int cuzk_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (g_refcount <= 0) return CUZK_OK;
   if (--g_refcount == 0) {
+    cudaDeviceSynchronize();
     for (int a = 0; a < 9; ++a) {
       if (g_d_pad[a]) cudaFree(g_d_pad[a]);
       g_d_pad[a] = nullptr;
       g_pad_levels[a] = 0;
+    }
+    {
+      std::lock_guard<std::mutex> lk2(g_hp_mu);
+      hp_stop();
     }
     g_device = -1;
   }
@@ -516,21 +752,14 @@ int cuzk_fr_batch(int op, const uint64_t *a, const uint64_t *b, uint64_t *out, s
   if (n == 0) return CUZK_OK;
   bool binary = op <= CUZK_FR_MUL;
   if (!a || !out || (binary && !b)) return fail(CUZK_ERR_INVALID, "null pointer");
-  cudaStream_t st = S(stream);
-  if (mem == CUZK_MEM_DEVICE) return fr_batch_dev(op, a, b, out, n, st);
-  DevBuf da, db, dout;
-  CK(da.alloc(n * 32));
-  CK(dout.alloc(n * 32));
-  CK(cudaMemcpyAsync(da.p, a, n * 32, cudaMemcpyHostToDevice, st));
-  if (binary) {
-    CK(db.alloc(n * 32));
-    CK(cudaMemcpyAsync(db.p, b, n * 32, cudaMemcpyHostToDevice, st));
-  }
-  rc = fr_batch_dev(op, da.as<uint64_t>(), db.as<uint64_t>(), dout.as<uint64_t>(), n, st);
-  if (rc) return rc;
-  CK(cudaMemcpyAsync(out, dout.p, n * 32, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  return CUZK_OK;
+  if (mem == CUZK_MEM_DEVICE) return fr_batch_dev(op, a, b, out, n, S(stream));
+  const void *in[2] = {a, b};
+  const size_t in_bytes[2] = {32, 32};
+  return host_pipeline(n, kCheapChunk, binary ? 2 : 1, in, in_bytes, out, 32, false,
+                       [&](cudaStream_t st, void **d_in, void *d_out, size_t m) {
+                         return fr_batch_dev(op, static_cast<const uint64_t *>(d_in[0]), static_cast<const uint64_t *>(d_in[1]),
+                                             static_cast<uint64_t *>(d_out), m, st);
+                       });
 }
 
 int cuzk_poseidon_hash_single(const uint64_t *in, uint64_t *out, size_t n, int mem, void *stream) {
@@ -538,21 +767,15 @@ int cuzk_poseidon_hash_single(const uint64_t *in, uint64_t *out, size_t n, int m
   if (rc) return rc;
   if (n == 0) return CUZK_OK;
   if (!in || !out) return fail(CUZK_ERR_INVALID, "null pointer");
-  cudaStream_t st = S(stream);
-  if (mem == CUZK_MEM_DEVICE) {
-    hash_single_kernel<<<grid_for(n, kBlock), kBlock, 0, st>>>(reinterpret_cast<const uint4 *>(in), reinterpret_cast<uint4 *>(out), n);
+  auto run = [](cudaStream_t st, const void *din, void *dout, size_t m) {
+    hash_single_kernel<<<grid_for(m, kBlock), kBlock, 0, st>>>(static_cast<const uint4 *>(din), static_cast<uint4 *>(dout), m);
     return check_launch("hash_single_kernel");
-  }
-  DevBuf din, dout;
-  CK(din.alloc(n * 32));
-  CK(dout.alloc(n * 32));
-  CK(cudaMemcpyAsync(din.p, in, n * 32, cudaMemcpyHostToDevice, st));
-  hash_single_kernel<<<grid_for(n, kBlock), kBlock, 0, st>>>(din.as<uint4>(), dout.as<uint4>(), n);
-  rc = check_launch("hash_single_kernel");
-  if (rc) return rc;
-  CK(cudaMemcpyAsync(out, dout.p, n * 32, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  return CUZK_OK;
+  };
+  if (mem == CUZK_MEM_DEVICE) return run(S(stream), in, out, n);
+  const void *ins[1] = {in};
+  const size_t in_bytes[1] = {32};
+  return host_pipeline(n, kHashChunk, 1, ins, in_bytes, out, 32, false,
+                       [&](cudaStream_t st, void **d_in, void *d_out, size_t m) { return run(st, d_in[0], d_out, m); });
 }
 
 int cuzk_poseidon_hash_pairs(const uint64_t *left, const uint64_t *right, uint64_t *out, size_t n, int mem, void *stream) {
@@ -560,24 +783,16 @@ int cuzk_poseidon_hash_pairs(const uint64_t *left, const uint64_t *right, uint64
   if (rc) return rc;
   if (n == 0) return CUZK_OK;
   if (!left || !right || !out) return fail(CUZK_ERR_INVALID, "null pointer");
-  cudaStream_t st = S(stream);
-  if (mem == CUZK_MEM_DEVICE) {
-    hash_pairs_kernel<<<grid_for(n, kBlock), kBlock, 0, st>>>(reinterpret_cast<const uint4 *>(left), reinterpret_cast<const uint4 *>(right),
-                                                             reinterpret_cast<uint4 *>(out), n);
+  auto run = [](cudaStream_t st, const void *dl, const void *dr, void *dout, size_t m) {
+    hash_pairs_kernel<<<grid_for(m, kBlock), kBlock, 0, st>>>(static_cast<const uint4 *>(dl), static_cast<const uint4 *>(dr),
+                                                             static_cast<uint4 *>(dout), m);
     return check_launch("hash_pairs_kernel");
-  }
-  DevBuf dl, dr, dout;
-  CK(dl.alloc(n * 32));
-  CK(dr.alloc(n * 32));
-  CK(dout.alloc(n * 32));
-  CK(cudaMemcpyAsync(dl.p, left, n * 32, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(dr.p, right, n * 32, cudaMemcpyHostToDevice, st));
-  hash_pairs_kernel<<<grid_for(n, kBlock), kBlock, 0, st>>>(dl.as<uint4>(), dr.as<uint4>(), dout.as<uint4>(), n);
-  rc = check_launch("hash_pairs_kernel");
-  if (rc) return rc;
-  CK(cudaMemcpyAsync(out, dout.p, n * 32, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  return CUZK_OK;
+  };
+  if (mem == CUZK_MEM_DEVICE) return run(S(stream), left, right, out, n);
+  const void *ins[2] = {left, right};
+  const size_t in_bytes[2] = {32, 32};
+  return host_pipeline(n, kHashChunk, 2, ins, in_bytes, out, 32, false,
+                       [&](cudaStream_t st, void **d_in, void *d_out, size_t m) { return run(st, d_in[0], d_in[1], d_out, m); });
 }
 
 int cuzk_poseidon_permutation(uint64_t *states, size_t n, int mem, void *stream) {
@@ -585,20 +800,15 @@ int cuzk_poseidon_permutation(uint64_t *states, size_t n, int mem, void *stream)
   if (rc) return rc;
   if (n == 0) return CUZK_OK;
   if (!states) return fail(CUZK_ERR_INVALID, "null pointer");
-  cudaStream_t st = S(stream);
-  if (mem == CUZK_MEM_DEVICE) {
-    permutation_kernel<<<grid_for(n, kBlock), kBlock, 0, st>>>(reinterpret_cast<uint4 *>(states), n);
+  auto run = [](cudaStream_t st, void *d, size_t m) {
+    permutation_kernel<<<grid_for(m, kBlock), kBlock, 0, st>>>(static_cast<uint4 *>(d), m);
     return check_launch("permutation_kernel");
-  }
-  DevBuf d;
-  CK(d.alloc(n * 96));
-  CK(cudaMemcpyAsync(d.p, states, n * 96, cudaMemcpyHostToDevice, st));
-  permutation_kernel<<<grid_for(n, kBlock), kBlock, 0, st>>>(d.as<uint4>(), n);
-  rc = check_launch("permutation_kernel");
-  if (rc) return rc;
-  CK(cudaMemcpyAsync(states, d.p, n * 96, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  return CUZK_OK;
+  };
+  if (mem == CUZK_MEM_DEVICE) return run(S(stream), states, n);
+  const void *ins[1] = {states};
+  const size_t in_bytes[1] = {96};
+  return host_pipeline(n, kHashChunk, 1, ins, in_bytes, states, 96, true,
+                       [&](cudaStream_t st, void **d_in, void *, size_t m) { return run(st, d_in[0], m); });
 }
 
 int cuzk_debug_mds_layer(uint64_t *states, size_t n, int mode, void *stream) {
@@ -615,22 +825,20 @@ int cuzk_poseidon_sponge(const uint64_t *in, size_t width, uint64_t ds, uint64_t
   if (width > 64) return fail(CUZK_ERR_INVALID, "sponge width must be <= 64");
   if (n == 0) return CUZK_OK;
   if (!out || (width && !in)) return fail(CUZK_ERR_INVALID, "null pointer");
-  cudaStream_t st = S(stream);
-  if (mem == CUZK_MEM_DEVICE) {
-    sponge_kernel<<<grid_for(n, kBlock), kBlock, 0, st>>>(reinterpret_cast<const uint4 *>(in), (int)width, (u32)ds, (u32)(ds >> 32),
-                                                         reinterpret_cast<uint4 *>(out), n);
+  auto run = [&](cudaStream_t st, const void *din, void *dout, size_t m) {
+    sponge_kernel<<<grid_for(m, kBlock), kBlock, 0, st>>>(static_cast<const uint4 *>(din), (int)width, (u32)ds, (u32)(ds >> 32),
+                                                         static_cast<uint4 *>(dout), m);
     return check_launch("sponge_kernel");
+  };
+  if (mem == CUZK_MEM_DEVICE) return run(S(stream), in, out, n);
+  if (width == 0) {  // zero permutations: every output is the zero element (poseidon.cpp:103-126)
+    memset(out, 0, n * 32);
+    return CUZK_OK;
   }
-  DevBuf din, dout;
-  CK(din.alloc(n * width * 32));
-  CK(dout.alloc(n * 32));
-  if (width) CK(cudaMemcpyAsync(din.p, in, n * width * 32, cudaMemcpyHostToDevice, st));
-  sponge_kernel<<<grid_for(n, kBlock), kBlock, 0, st>>>(din.as<uint4>(), (int)width, (u32)ds, (u32)(ds >> 32), dout.as<uint4>(), n);
-  rc = check_launch("sponge_kernel");
-  if (rc) return rc;
-  CK(cudaMemcpyAsync(out, dout.p, n * 32, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  return CUZK_OK;
+  const void *ins[1] = {in};
+  const size_t in_bytes[1] = {32 * width};
+  return host_pipeline(n, kHashChunk, 1, ins, in_bytes, out, 32, false,
+                       [&](cudaStream_t st, void **d_in, void *d_out, size_t m) { return run(st, d_in[0], d_out, m); });
 }
 
 // ---- Merkle geometry ----
@@ -677,14 +885,14 @@ int cuzk_merkle_build(const uint64_t *leaves, size_t n, unsigned arity, uint64_t
   if (!leaves || !levels_out) return fail(CUZK_ERR_INVALID, "null pointer");
   cudaStream_t st = S(stream);
   if (mem == CUZK_MEM_DEVICE) return merkle_build_dev(leaves, n, arity, levels_out, st);
+  std::lock_guard<std::mutex> lk(g_hp_mu);
   size_t tot = cuzk_merkle_total_nodes(n, arity);
-  DevBuf dl, dv;
-  CK(dl.alloc(n * 32));
-  CK(dv.alloc(tot * 32));
-  CK(cudaMemcpyAsync(dl.p, leaves, n * 32, cudaMemcpyHostToDevice, st));
-  rc = merkle_build_dev(dl.as<uint64_t>(), n, arity, dv.as<uint64_t>(), st);
+  void *dl, *dv;
+  if ((rc = ws_get(0, n * 32, &dl)) || (rc = ws_get(1, tot * 32, &dv))) return rc;
+  CK(cudaMemcpyAsync(dl, leaves, n * 32, cudaMemcpyHostToDevice, st));
+  rc = merkle_build_dev(static_cast<uint64_t *>(dl), n, arity, static_cast<uint64_t *>(dv), st);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(levels_out, dv.p, tot * 32, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(levels_out, dv, tot * 32, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return CUZK_OK;
 }
@@ -696,51 +904,14 @@ int cuzk_merkle_subtree_roots(const uint64_t *leaves, size_t n, unsigned arity, 
   if ((rc = check_arity(arity))) return rc;
   if (count == 0) return CUZK_OK;
   if (mem != CUZK_MEM_DEVICE) return fail(CUZK_ERR_INVALID, "cuzk_merkle_subtree_roots: device pointers only");
-  if ((rc = ensure_padding(arity))) return rc;
-  if ((int)height >= g_pad_levels[arity]) return fail(CUZK_ERR_INVALID, "subtree too tall");
+  if (!roots_out || (n && !leaves)) return fail(CUZK_ERR_INVALID, "null pointer");
   size_t span = 1;
-  for (unsigned i = 0; i < height; ++i) span *= arity;
+  for (unsigned i = 0; i < height; ++i) {
+    if (span > (~(size_t)0) / arity) return fail(CUZK_ERR_INVALID, "subtree too tall");
+    span *= arity;
+  }
   if (n > count * span) return fail(CUZK_ERR_INVALID, "more leaves than the subtrees hold");
-  cudaStream_t st = S(stream);
-  const uint4 *pad = reinterpret_cast<const uint4 *>(g_d_pad[arity]);
-  if (height == 0) {
-    merkle_pad_leaves_kernel<<<grid_for(count, 256), 256, 0, st>>>(reinterpret_cast<const uint4 *>(leaves), n, count, pad,
-                                                                  reinterpret_cast<uint4 *>(roots_out));
-    return check_launch("merkle_pad_leaves_kernel");
-  }
-  // ping-pong scratch holding one level at a time; only the final level reaches roots_out
-  size_t p = count * span / arity;  // nodes of level 1
-  DevBuf s0, s1;
-  if (height > 1) {
-    CK(s0.alloc(p * 32));
-    if (height > 2) CK(s1.alloc((p / arity) * 32));
-  }
-  const uint4 *cur = reinterpret_cast<const uint4 *>(leaves);
-  size_t real = n;
-  for (unsigned l = 1; l <= height; ++l) {
-    uint4 *dst = (l == height) ? reinterpret_cast<uint4 *>(roots_out) : ((l & 1) ? s0.as<uint4>() : s1.as<uint4>());
-    real = (real + arity - 1) / arity;
-    // level-1 reads real leaves only: children beyond n are virtual padding, so hash groups that straddle n
-    // through a padded copy.  Simple approach: the first level pads on the fly via merkle_level_kernel's
-    // contract (inputs must exist), so materialise the straddling group when n is not a multiple of arity.
-    if (l == 1 && n % arity != 0) {
-      // copy leaves into a padded buffer of real*arity elements
-      DevBuf padded;
-      CK(padded.alloc(real * arity * 32));
-      merkle_pad_leaves_kernel<<<grid_for(real * arity, 256), 256, 0, st>>>(cur, n, real * arity, pad, padded.as<uint4>());
-      if ((rc = check_launch("merkle_pad_leaves_kernel"))) return rc;
-      merkle_level_kernel<<<grid_for(p, kBlock), kBlock, 0, st>>>(padded.as<uint4>(), dst, real, p, (int)arity, pad + 2 * l);
-      if ((rc = check_launch("merkle_level_kernel"))) return rc;
-      CK(cudaStreamSynchronize(st));  // `padded` is freed at scope exit
-    } else {
-      merkle_level_kernel<<<grid_for(p, kBlock), kBlock, 0, st>>>(cur, dst, real, p, (int)arity, pad + 2 * l);
-      if ((rc = check_launch("merkle_level_kernel"))) return rc;
-    }
-    cur = dst;
-    p /= arity;
-  }
-  CK(cudaStreamSynchronize(st));  // scratch is released on return
-  return CUZK_OK;
+  return subtree_roots_dev(leaves, n, arity, height, count, roots_out, S(stream));
 }
 
 int cuzk_merkle_top_root(const uint64_t *nodes, size_t count, unsigned arity, uint64_t *root_out, int mem, void *stream) {
@@ -752,15 +923,15 @@ int cuzk_merkle_top_root(const uint64_t *nodes, size_t count, unsigned arity, ui
   unsigned h = 0;
   while (p < count) { p *= arity; ++h; }
   if (p != count) return fail(CUZK_ERR_INVALID, "count must be a power of arity");
-  if (mem == CUZK_MEM_DEVICE) return cuzk_merkle_subtree_roots(nodes, count, arity, h, 1, root_out, mem, stream);
   cudaStream_t st = S(stream);
-  DevBuf dn, dr;
-  CK(dn.alloc(count * 32));
-  CK(dr.alloc(32));
-  CK(cudaMemcpyAsync(dn.p, nodes, count * 32, cudaMemcpyHostToDevice, st));
-  rc = cuzk_merkle_subtree_roots(dn.as<uint64_t>(), count, arity, h, 1, dr.as<uint64_t>(), CUZK_MEM_DEVICE, stream);
+  if (mem == CUZK_MEM_DEVICE) return subtree_roots_dev(nodes, count, arity, h, 1, root_out, st);
+  std::lock_guard<std::mutex> lk(g_hp_mu);
+  void *dn, *dr;
+  if ((rc = ws_get(0, count * 32, &dn)) || (rc = ws_get(1, 32, &dr))) return rc;
+  CK(cudaMemcpyAsync(dn, nodes, count * 32, cudaMemcpyHostToDevice, st));
+  rc = subtree_roots_dev(static_cast<uint64_t *>(dn), count, arity, h, 1, static_cast<uint64_t *>(dr), st);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(root_out, dr.p, 32, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(root_out, dr, 32, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return CUZK_OK;
 }
@@ -783,19 +954,20 @@ int cuzk_merkle_prove_batch(const uint64_t *levels, size_t n, unsigned arity, co
                                                                 indices, num_proofs, reinterpret_cast<uint4 *>(siblings_out), positions_out);
     return check_launch("merkle_prove_kernel");
   }
+  std::lock_guard<std::mutex> lk(g_hp_mu);
   size_t tot = cuzk_merkle_total_nodes(n, arity);
-  DevBuf dl, di, ds, dp;
-  CK(dl.alloc(tot * 32));
-  CK(di.alloc(num_proofs * 8));
-  CK(ds.alloc(threads * (arity - 1) * 32));
-  CK(dp.alloc(threads * 4));
-  CK(cudaMemcpyAsync(dl.p, levels, tot * 32, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(di.p, indices, num_proofs * 8, cudaMemcpyHostToDevice, st));
-  merkle_prove_kernel<<<grid_for(threads, 256), 256, 0, st>>>(dl.as<uint4>(), n, padded, (int)arity, (int)nlv, di.as<u64>(), num_proofs,
-                                                              ds.as<uint4>(), dp.as<u32>());
+  void *dl, *di, *ds, *dp;
+  if ((rc = ws_get(0, tot * 32, &dl)) || (rc = ws_get(1, num_proofs * 8, &di)) || (rc = ws_get(2, threads * (arity - 1) * 32, &ds)) ||
+      (rc = ws_get(3, threads * 4, &dp)))
+    return rc;
+  CK(cudaMemcpyAsync(dl, levels, tot * 32, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(di, indices, num_proofs * 8, cudaMemcpyHostToDevice, st));
+  merkle_prove_kernel<<<grid_for(threads, 256), 256, 0, st>>>(static_cast<uint4 *>(dl), n, padded, (int)arity, (int)nlv,
+                                                              static_cast<u64 *>(di), num_proofs, static_cast<uint4 *>(ds),
+                                                              static_cast<u32 *>(dp));
   if ((rc = check_launch("merkle_prove_kernel"))) return rc;
-  CK(cudaMemcpyAsync(siblings_out, ds.p, threads * (arity - 1) * 32, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(positions_out, dp.p, threads * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(siblings_out, ds, threads * (arity - 1) * 32, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(positions_out, dp, threads * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return CUZK_OK;
 }
@@ -814,25 +986,22 @@ int cuzk_merkle_verify_batch(const uint64_t *leaf_values, const uint64_t *siblin
                                                                          (int)arity, reinterpret_cast<const uint4 *>(root), results_out, num_proofs);
     return check_launch("merkle_verify_kernel");
   }
-  size_t sib_bytes = num_proofs * levels * (arity - 1) * 32, pos_bytes = num_proofs * levels * 4;
-  DevBuf dl, ds, dp, dr, dres;
-  CK(dl.alloc(num_proofs * 32));
-  CK(ds.alloc(sib_bytes));
-  CK(dp.alloc(pos_bytes));
-  CK(dr.alloc(32));
-  CK(dres.alloc(num_proofs));
-  CK(cudaMemcpyAsync(dl.p, leaf_values, num_proofs * 32, cudaMemcpyHostToDevice, st));
-  if (levels) {
-    CK(cudaMemcpyAsync(ds.p, siblings, sib_bytes, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(dp.p, positions, pos_bytes, cudaMemcpyHostToDevice, st));
+  void *droot;
+  {
+    std::lock_guard<std::mutex> lk(g_hp_mu);
+    if ((rc = ws_get(4, 32, &droot))) return rc;
+    CK(cudaMemcpy(droot, root, 32, cudaMemcpyHostToDevice));
   }
-  CK(cudaMemcpyAsync(dr.p, root, 32, cudaMemcpyHostToDevice, st));
-  merkle_verify_kernel<<<grid_for(num_proofs, kBlock), kBlock, 0, st>>>(dl.as<uint4>(), ds.as<uint4>(), dp.as<u32>(), (int)levels, (int)arity,
-                                                                       dr.as<uint4>(), dres.as<uint8_t>(), num_proofs);
-  if ((rc = check_launch("merkle_verify_kernel"))) return rc;
-  CK(cudaMemcpyAsync(results_out, dres.p, num_proofs, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  return CUZK_OK;
+  const void *ins[3] = {leaf_values, siblings, positions};
+  const size_t in_bytes[3] = {32, levels * (arity - 1) * 32, levels * 4};
+  // proofs are independent: chunk them like hashes (each costs levels x ceil(arity/2) permutations)
+  return host_pipeline(num_proofs, kHashChunk, levels ? 3 : 1, ins, in_bytes, results_out, 1, false,
+                       [&](cudaStream_t s2, void **d_in, void *d_out, size_t m) {
+                         merkle_verify_kernel<<<grid_for(m, kBlock), kBlock, 0, s2>>>(
+                             static_cast<const uint4 *>(d_in[0]), static_cast<const uint4 *>(d_in[1]), static_cast<const u32 *>(d_in[2]),
+                             (int)levels, (int)arity, static_cast<const uint4 *>(droot), static_cast<uint8_t *>(d_out), m);
+                         return check_launch("merkle_verify_kernel");
+                       });
 }
 
 int cuzk_synth_elements(uint64_t *out, size_t n, uint64_t seed, uint64_t start, int canonical, void *stream) {

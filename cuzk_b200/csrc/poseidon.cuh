@@ -99,7 +99,15 @@ __device__ __forceinline__ void mds_row(u32 (&n)[8], const u32 (&s0)[8], const u
 }
 
 // exact MDS layer, term by term as the reference evaluates it (also the fallback of mds_fast)
-__device__ __noinline__ void mds_exact(u32 (&s0)[8], u32 (&s1)[8], u32 (&s2)[8]) {
+#ifndef CUZK_MDS_EXACT_INLINE
+#define CUZK_MDS_EXACT_INLINE 1
+#endif
+#if CUZK_MDS_EXACT_INLINE
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+void mds_exact(u32 (&s0)[8], u32 (&s1)[8], u32 (&s2)[8]) {
   u32 n0[8], n1[8], n2[8];
   mds_row<7, 23, 8>(n0, s0, s1, s2);
   mds_row<26, 5, 4>(n1, s0, s1, s2);
