@@ -671,6 +671,20 @@ int cuzk_device_count(void) {
 
 int cuzk_is_initialized(void) { return g_refcount > 0 ? 1 : 0; }
 
+int cuzk_device_info(int device, cuzk_device_info_t *out) {
+  if (!out) return fail(CUZK_ERR_INVALID, "null pointer");
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  memset(out, 0, sizeof *out);
+  strncpy(out->name, prop.name, sizeof out->name - 1);
+  out->cc_major = prop.major;
+  out->cc_minor = prop.minor;
+  out->sm_count = prop.multiProcessorCount;
+  out->max_threads_per_block = prop.maxThreadsPerBlock;
+  out->total_mem_bytes = prop.totalGlobalMem;
+  return CUZK_OK;
+}
+
 int cuzk_init(int device) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (g_refcount > 0) {

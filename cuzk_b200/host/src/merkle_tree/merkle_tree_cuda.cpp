@@ -1,0 +1,324 @@
+// merkle_tree_cuda.cpp -- CudaNaryMerkleTree over the C ABI (replaces src/merkle_tree/merkle_tree_cuda.cu:120-740; its two
+// kernels, :45-118, are in libcuzk_b200.so).  Host C++ only: marshals std::vector data to the flat layouts the C ABI takes.
+#include "merkle_tree_cuda.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <iostream>
+#include <map>
+#include <mutex>
+#include <random>
+
+#include "cuzk_b200.h"
+
+namespace MerkleTree {
+namespace MerkleTreeCUDA {
+
+namespace {
+
+std::mutex g_mu;
+int g_init_refs = 0;  // references this translation unit holds on the library through initialize_cuda()
+
+const uint64_t *raw(const std::vector<FieldElement> &v) { return reinterpret_cast<const uint64_t *>(v.data()); }
+uint64_t *raw(std::vector<FieldElement> &v) { return reinterpret_cast<uint64_t *>(v.data()); }
+
+bool ensure_library() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_init_refs > 0) return true;
+  if (cuzk_init(0) != CUZK_OK) {
+    std::cerr << "Failed to initialize CUDA Poseidon: " << cuzk_last_error() << std::endl;
+    return false;
+  }
+  g_init_refs = 1;
+  return true;
+}
+
+}  // namespace
+
+CudaNaryMerkleTree::CudaNaryMerkleTree(const MerkleTreeConfig &config) : config_(config), leaf_count_(0), tree_height_(0) {
+  ensure_library();
+}
+
+CudaNaryMerkleTree::CudaNaryMerkleTree(const std::vector<FieldElement> &leaves, const MerkleTreeConfig &config)
+    : config_(config), leaf_count_(0), tree_height_(0) {
+  ensure_library();
+  build_tree(leaves);
+}
+
+CudaNaryMerkleTree::~CudaNaryMerkleTree() = default;
+
+bool CudaNaryMerkleTree::build_tree(const std::vector<FieldElement> &leaves) {
+  tree_levels_.clear();
+  if (leaves.empty()) {  // an empty input clears the tree (merkle_tree_cuda.cu:142-148)
+    leaf_count_ = 0;
+    tree_height_ = 0;
+    leaves_.clear();
+    return true;
+  }
+  if (!ensure_library()) return false;
+  const unsigned arity = (unsigned)config_.arity;
+  const size_t n = leaves.size();
+  std::vector<FieldElement> flat(cuzk_merkle_total_nodes(n, arity));
+  if (cuzk_merkle_build(raw(leaves), n, arity, raw(flat), CUZK_MEM_HOST, nullptr) != CUZK_OK) {
+    std::cerr << "CudaNaryMerkleTree::build_tree: " << cuzk_last_error() << std::endl;
+    leaf_count_ = 0;
+    tree_height_ = 0;
+    leaves_.clear();
+    return false;
+  }
+  leaves_ = leaves;
+  leaf_count_ = n;
+  tree_height_ = cuzk_merkle_tree_height(n, arity);  // the reference's float formula: a getter value only
+  const size_t nlevels = cuzk_merkle_num_levels(n, arity);
+  tree_levels_.reserve(nlevels);
+  size_t width = cuzk_merkle_padded_leaves(n, arity), at = 0;
+  for (size_t l = 0; l < nlevels; ++l) {
+    tree_levels_.emplace_back(flat.begin() + at, flat.begin() + at + width);
+    at += width;
+    width /= arity;
+  }
+  return true;
+}
+
+std::optional<MerkleProof> CudaNaryMerkleTree::generate_proof(size_t leaf_index) const {
+  if (leaf_index >= leaf_count_ || tree_levels_.empty()) return std::nullopt;
+  const size_t arity = config_.arity, nlv = tree_levels_.size() - 1;
+  MerkleProof proof;
+  proof.leaf_index = leaf_index;
+  proof.path.resize(nlv);
+  proof.indices.resize(nlv);
+  size_t idx = leaf_index;
+  for (size_t l = 0; l < nlv; ++l) {
+    const size_t slot = idx % arity, first = idx - slot;
+    const std::vector<FieldElement> &level = tree_levels_[l];
+    std::vector<FieldElement> &sib = proof.path[l];
+    sib.reserve(arity - 1);
+    for (size_t c = 0; c < arity; ++c)
+      if (c != slot) sib.push_back(level[first + c]);
+    proof.indices[l] = slot;
+    idx /= arity;
+  }
+  return proof;
+}
+
+std::vector<MerkleProof> CudaNaryMerkleTree::generate_batch_proofs(const std::vector<size_t> &indices) const {
+  std::vector<MerkleProof> proofs;
+  proofs.reserve(indices.size());
+  for (size_t i : indices) {
+    auto p = generate_proof(i);
+    if (p) proofs.push_back(std::move(*p));  // invalid indices are skipped silently, as in the reference
+  }
+  return proofs;
+}
+
+bool CudaNaryMerkleTree::verify_batch_proofs_each(const std::vector<MerkleProof> &proofs, const std::vector<FieldElement> &leaf_values,
+                                                  std::vector<uint8_t> &results) const {
+  results.assign(proofs.size(), 0);
+  if (proofs.size() != leaf_values.size() || proofs.empty() || tree_levels_.empty()) return false;
+  if (!ensure_library()) return false;
+  const size_t arity = config_.arity, sib_per_level = arity - 1;
+  const FieldElement root = get_root_hash();
+  const FieldElement filler = compute_empty_hash(arity);  // stands in for a missing sibling (merkle_tree_cuda.cu:312-315)
+  // Proofs of equal length go to the GPU as one level-uniform batch; a proof whose path and indices disagree in length
+  // is rejected outright (the reference would read past the end of `indices`).
+  std::map<size_t, std::vector<size_t>> by_len;
+  for (size_t q = 0; q < proofs.size(); ++q)
+    if (proofs[q].path.size() == proofs[q].indices.size()) by_len[proofs[q].path.size()].push_back(q);
+  for (const auto &group : by_len) {
+    const size_t L = group.first, m = group.second.size();
+    std::vector<FieldElement> leaves(m), sib(m * L * sib_per_level, filler);
+    std::vector<uint32_t> pos(m * L);
+    for (size_t k = 0; k < m; ++k) {
+      const MerkleProof &p = proofs[group.second[k]];
+      leaves[k] = leaf_values[group.second[k]];
+      for (size_t l = 0; l < L; ++l) {
+        pos[k * L + l] = p.indices[l] < arity ? (uint32_t)p.indices[l] : 0xFFFFFFFFu;
+        const size_t have = std::min(p.path[l].size(), sib_per_level);
+        std::copy(p.path[l].begin(), p.path[l].begin() + have, sib.begin() + (k * L + l) * sib_per_level);
+      }
+    }
+    std::vector<uint8_t> res(m);
+    if (cuzk_merkle_verify_batch(raw(leaves), raw(sib), pos.data(), L, (unsigned)arity, root.limbs, res.data(), m, CUZK_MEM_HOST, nullptr) !=
+        CUZK_OK) {
+      std::cerr << "CudaNaryMerkleTree::verify_batch_proofs: " << cuzk_last_error() << std::endl;
+      return false;
+    }
+    for (size_t k = 0; k < m; ++k) results[group.second[k]] = res[k];
+  }
+  return true;
+}
+
+bool CudaNaryMerkleTree::verify_batch_proofs(const std::vector<MerkleProof> &proofs, const std::vector<FieldElement> &leaf_values) const {
+  std::vector<uint8_t> results;
+  if (!verify_batch_proofs_each(proofs, leaf_values, results)) return false;
+  return std::all_of(results.begin(), results.end(), [](uint8_t r) { return r != 0; });
+}
+
+bool CudaNaryMerkleTree::verify_proof(const MerkleProof &proof, const FieldElement &leaf_value) const {
+  if (tree_levels_.empty()) return false;
+  return verify_batch_proofs(std::vector<MerkleProof>{proof}, std::vector<FieldElement>{leaf_value});
+}
+
+bool CudaNaryMerkleTree::build_batch_trees(const std::vector<std::vector<FieldElement>> &batch_leaves, std::vector<CudaNaryMerkleTree> &trees,
+                                           const MerkleTreeConfig &config) {
+  trees.clear();
+  trees.reserve(batch_leaves.size());
+  for (const auto &leaves : batch_leaves) {
+    CudaNaryMerkleTree tree(config);
+    if (!tree.build_tree(leaves)) return false;
+    trees.push_back(std::move(tree));
+  }
+  return true;
+}
+
+FieldElement CudaNaryMerkleTree::get_root_hash() const {
+  if (tree_levels_.empty() || tree_levels_.back().empty()) return compute_empty_hash(config_.arity);
+  return tree_levels_.back()[0];
+}
+
+FieldElement CudaNaryMerkleTree::compute_empty_hash(size_t arity) const {
+  FieldElement e;
+  if (!ensure_library() || cuzk_merkle_empty_hash((unsigned)arity, e.limbs) != CUZK_OK)
+    std::cerr << "CudaNaryMerkleTree: empty hash unavailable: " << cuzk_last_error() << std::endl;
+  return e;
+}
+
+void CudaNaryMerkleTree::print_tree() const {
+  std::cout << "CUDA Merkle Tree (arity=" << config_.arity << ", height=" << tree_height_ << "):" << std::endl;
+  for (size_t l = tree_levels_.size(); l-- > 0;) {
+    const auto &level = tree_levels_[l];
+    std::cout << "Level " << l << ": ";
+    for (size_t i = 0; i < std::min<size_t>(level.size(), 8); ++i) std::cout << level[i].to_hex().substr(0, 8) << "... ";
+    if (level.size() > 8) std::cout << "(+" << (level.size() - 8) << " more)";
+    std::cout << std::endl;
+  }
+}
+
+bool CudaNaryMerkleTree::initialize_cuda() { return ensure_library(); }
+
+void CudaNaryMerkleTree::cleanup_cuda() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_init_refs == 0) return;
+  g_init_refs = 0;
+  cuzk_shutdown();  // one reference; the library stays up while hashers or CudaFieldArithmetic still hold theirs
+}
+
+size_t CudaNaryMerkleTree::get_optimal_batch_size() {
+  cuzk_device_info_t info;
+  if (cuzk_device_info(0, &info) != CUZK_OK) return 1024;
+  return (size_t)info.sm_count * 7 * 128;
+}
+size_t CudaNaryMerkleTree::get_max_batch_size() { return (size_t)1 << 31; }
+
+namespace CudaMerkleUtils {
+
+MerkleTreeConfig get_optimal_config_for_gpu(size_t leaf_count) {
+  // wider nodes mean fewer levels and fewer permutations per leaf: arity 2 costs 1 permutation per leaf, arity 8 costs 4/7
+  const size_t arity = leaf_count < 1000 ? 2 : (leaf_count > 100000 ? 8 : 4);
+  return MerkleTreeConfig(arity, cuzk_merkle_tree_height(leaf_count, (unsigned)arity));
+}
+
+bool check_cuda_compatibility() {
+  if (cuzk_device_count() <= 0) {
+    std::cerr << "No CUDA-capable devices found" << std::endl;
+    return false;
+  }
+  cuzk_device_info_t info;
+  if (cuzk_device_info(0, &info) != CUZK_OK) return false;
+  if (info.cc_major < 10) {
+    std::cerr << "cuzk_b200 needs a compute capability 10.0 (B200) device, found " << info.cc_major << "." << info.cc_minor << std::endl;
+    return false;
+  }
+  return true;
+}
+
+std::vector<std::vector<FieldElement>> generate_batch_test_leaves(size_t num_trees, size_t leaves_per_tree, uint64_t seed) {
+  std::vector<std::vector<FieldElement>> batch(num_trees);
+  for (size_t t = 0; t < num_trees; ++t) {
+    batch[t].reserve(leaves_per_tree);
+    for (size_t i = 0; i < leaves_per_tree; ++i) batch[t].emplace_back(seed + t * leaves_per_tree + i);  // merkle_tree_cuda.cu:623-643
+  }
+  return batch;
+}
+
+}  // namespace CudaMerkleUtils
+
+namespace {
+double ms_since(std::chrono::steady_clock::time_point t0) {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+CudaMerkleTreeStats fresh_stats(size_t leaves, size_t arity) {
+  CudaMerkleTreeStats s = {};
+  s.leaf_count = leaves;
+  s.arity = arity;
+  return s;
+}
+}  // namespace
+
+CudaMerkleTreeStats benchmark_cuda_tree_building(size_t num_trees, size_t leaves_per_tree, size_t arity, size_t /*batch_size*/) {
+  CudaMerkleTreeStats stats = fresh_stats(leaves_per_tree, arity);
+  stats.total_trees = num_trees;
+  if (!CudaNaryMerkleTree::initialize_cuda()) return stats;
+  const auto batch = CudaMerkleUtils::generate_batch_test_leaves(num_trees, leaves_per_tree, 12345);
+  std::vector<CudaNaryMerkleTree> trees;
+  const auto t0 = std::chrono::steady_clock::now();
+  const bool ok = CudaNaryMerkleTree::build_batch_trees(batch, trees, MerkleTreeConfig(arity));
+  const double ms = ms_since(t0);
+  if (!ok || trees.empty()) {
+    std::cerr << "CUDA tree building failed" << std::endl;
+    return stats;
+  }
+  stats.build_time_ms = stats.total_time_ms = ms;
+  stats.tree_height = trees[0].get_tree_height();
+  if (ms > 0) stats.trees_per_second = static_cast<size_t>(num_trees * 1000.0 / ms);
+  return stats;
+}
+
+namespace {
+std::vector<size_t> random_indices(size_t count, size_t bound) {
+  std::mt19937_64 gen(std::random_device{}());
+  std::uniform_int_distribution<size_t> pick(0, bound - 1);
+  std::vector<size_t> idx(count);
+  for (auto &i : idx) i = pick(gen);
+  return idx;
+}
+}  // namespace
+
+CudaMerkleTreeStats benchmark_cuda_proof_generation(size_t num_proofs, size_t leaves_per_tree, size_t arity, size_t /*batch_size*/) {
+  CudaMerkleTreeStats stats = fresh_stats(leaves_per_tree, arity);
+  stats.total_proofs = num_proofs;
+  if (!CudaNaryMerkleTree::initialize_cuda() || leaves_per_tree == 0) return stats;
+  CudaNaryMerkleTree tree(CudaMerkleUtils::generate_batch_test_leaves(1, leaves_per_tree, 54321)[0], MerkleTreeConfig(arity));
+  stats.tree_height = tree.get_tree_height();
+  const auto idx = random_indices(num_proofs, leaves_per_tree);
+  const auto t0 = std::chrono::steady_clock::now();
+  const auto proofs = tree.generate_batch_proofs(idx);
+  const double ms = ms_since(t0);
+  stats.proof_generation_time_ms = stats.total_time_ms = ms;
+  if (ms > 0) stats.proofs_per_second = static_cast<size_t>(proofs.size() * 1000.0 / ms);
+  return stats;
+}
+
+CudaMerkleTreeStats benchmark_cuda_proof_verification(size_t num_proofs, size_t leaves_per_tree, size_t arity, size_t /*batch_size*/) {
+  CudaMerkleTreeStats stats = fresh_stats(leaves_per_tree, arity);
+  stats.total_proofs = num_proofs;
+  if (!CudaNaryMerkleTree::initialize_cuda() || leaves_per_tree == 0) return stats;
+  const auto leaves = CudaMerkleUtils::generate_batch_test_leaves(1, leaves_per_tree, 98765)[0];
+  CudaNaryMerkleTree tree(leaves, MerkleTreeConfig(arity));
+  stats.tree_height = tree.get_tree_height();
+  const auto idx = random_indices(num_proofs, leaves_per_tree);
+  std::vector<FieldElement> values;
+  values.reserve(num_proofs);
+  for (size_t i : idx) values.push_back(leaves[i]);
+  const auto proofs = tree.generate_batch_proofs(idx);
+  const auto t0 = std::chrono::steady_clock::now();
+  const bool ok = tree.verify_batch_proofs(proofs, values);
+  const double ms = ms_since(t0);
+  stats.proof_verification_time_ms = stats.total_time_ms = ms;
+  if (ms > 0) stats.proofs_per_second = static_cast<size_t>(num_proofs * 1000.0 / ms);
+  if (!ok) std::cerr << "Warning: Batch proof verification failed in benchmark" << std::endl;
+  return stats;
+}
+
+}  // namespace MerkleTreeCUDA
+}  // namespace MerkleTree

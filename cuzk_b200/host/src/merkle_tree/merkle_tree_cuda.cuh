@@ -1,0 +1,116 @@
+// merkle_tree/merkle_tree_cuda.cuh -- CudaNaryMerkleTree: GPU build, proofs and batch verification.
+//
+// Replaces the reference's src/merkle_tree/merkle_tree_cuda.cuh:39-151 (same class, benchmark helpers and utility
+// namespace).  The two reference kernels (:24-36) are gone from the header: building, proving and verifying run in
+// libcuzk_b200.so through cuzk_merkle_build / cuzk_merkle_verify_batch (include/cuzk_b200.h).
+//
+// Behaviour kept from the reference class: leaves are stored un-hashed and padded with empty_hash(arity) to a power
+// of the arity; get_tree_levels() exposes every level on the host (level 0 = padded leaves, last = root);
+// verify_proof compares against the tree's own root; verify_batch_proofs returns false for an empty batch or a
+// size mismatch; get_tree_height() returns the reference's floating-point formula.
+// Deliberate differences: the level arrays are sized by the integer padding loop, never by the float height (the
+// reference builds a spurious extra level at exact powers); the whole tree is built in one
+// host call (one upload, one download) instead of a PCIe round trip per level; batches of every size are verified
+// on the GPU (the reference verifies fewer than 32 proofs on the CPU, merkle_tree_cuda.cu:348-355).
+#pragma once
+
+#include <memory>
+#include <optional>
+#include <vector>
+
+#include "../poseidon/cuda/cuda_field_element.cuh"
+#include "../poseidon/cuda/poseidon_cuda.cuh"
+#include "merkle_tree.hpp"
+
+namespace MerkleTree {
+namespace MerkleTreeCUDA {
+
+using CudaFieldElement = Poseidon::CudaFieldElement;
+
+struct CudaMerkleTreeStats;
+
+class CudaNaryMerkleTree {
+private:
+  MerkleTreeConfig config_;
+  std::vector<FieldElement> leaves_;
+  std::vector<std::vector<FieldElement>> tree_levels_;
+  size_t leaf_count_;
+  size_t tree_height_;
+
+  FieldElement compute_empty_hash(size_t arity) const;
+
+public:
+  explicit CudaNaryMerkleTree(const MerkleTreeConfig &config = MerkleTreeConfig());
+  explicit CudaNaryMerkleTree(const std::vector<FieldElement> &leaves, const MerkleTreeConfig &config = MerkleTreeConfig());
+  ~CudaNaryMerkleTree();
+  CudaNaryMerkleTree(CudaNaryMerkleTree &&) = default;
+  CudaNaryMerkleTree &operator=(CudaNaryMerkleTree &&) = default;
+  CudaNaryMerkleTree(const CudaNaryMerkleTree &) = default;
+  CudaNaryMerkleTree &operator=(const CudaNaryMerkleTree &) = default;
+
+  bool build_tree(const std::vector<FieldElement> &leaves);
+
+  std::optional<MerkleProof> generate_proof(size_t leaf_index) const;
+  bool verify_proof(const MerkleProof &proof, const FieldElement &leaf_value) const;
+
+  std::vector<MerkleProof> generate_batch_proofs(const std::vector<size_t> &indices) const;
+  bool verify_batch_proofs(const std::vector<MerkleProof> &proofs, const std::vector<FieldElement> &leaf_values) const;
+  // extension: per-proof verdicts (1 = valid) instead of their conjunction
+  bool verify_batch_proofs_each(const std::vector<MerkleProof> &proofs, const std::vector<FieldElement> &leaf_values,
+                                std::vector<uint8_t> &results) const;
+
+  static bool build_batch_trees(const std::vector<std::vector<FieldElement>> &batch_leaves, std::vector<CudaNaryMerkleTree> &trees,
+                                const MerkleTreeConfig &config = MerkleTreeConfig());
+
+  FieldElement get_root_hash() const;
+  size_t get_leaf_count() const { return leaf_count_; }
+  size_t get_tree_height() const { return tree_height_; }
+  size_t get_arity() const { return config_.arity; }
+  const std::vector<FieldElement> &get_leaves() const { return leaves_; }
+  const std::vector<std::vector<FieldElement>> &get_tree_levels() const { return tree_levels_; }
+
+  void print_tree() const;
+
+  // root / leaf count / arity equality with the reference's CPU tree.  A template so that this header does not need the
+  // CPU class to be complete; it is instantiated only by callers that have the CPU tree (the reference's tests do).
+  template <class CpuTree = NaryMerkleTree>
+  bool compare_with_cpu_tree(const CpuTree &cpu_tree) const {
+    if (get_leaf_count() != cpu_tree.get_leaf_count() || get_arity() != cpu_tree.get_arity()) return false;
+    return get_root_hash() == cpu_tree.get_root_hash();
+  }
+
+  static bool initialize_cuda();
+  static void cleanup_cuda();
+  static size_t get_optimal_batch_size();
+  static size_t get_max_batch_size();
+};
+
+struct CudaMerkleTreeStats {
+  double total_time_ms;
+  double build_time_ms;
+  double proof_generation_time_ms;
+  double proof_verification_time_ms;
+  size_t trees_per_second;
+  size_t proofs_per_second;
+  size_t total_trees;
+  size_t total_proofs;
+  double speedup_vs_cpu;
+  size_t leaf_count;
+  size_t tree_height;
+  size_t arity;
+};
+
+CudaMerkleTreeStats benchmark_cuda_tree_building(size_t num_trees, size_t leaves_per_tree, size_t arity = 2, size_t batch_size = 32);
+CudaMerkleTreeStats benchmark_cuda_proof_generation(size_t num_proofs, size_t leaves_per_tree, size_t arity = 2, size_t batch_size = 256);
+CudaMerkleTreeStats benchmark_cuda_proof_verification(size_t num_proofs, size_t leaves_per_tree, size_t arity = 2, size_t batch_size = 512);
+// needs the reference's CPU tree at link time; lives in its own source file (merkle_tree_cuda_vs_cpu.cpp)
+CudaMerkleTreeStats benchmark_cuda_vs_cpu_merkle(size_t num_trees, size_t leaves_per_tree, size_t arity = 2, size_t batch_size = 32);
+
+namespace CudaMerkleUtils {
+MerkleTreeConfig get_optimal_config_for_gpu(size_t leaf_count);
+bool check_cuda_compatibility();
+std::vector<std::vector<FieldElement>> generate_batch_test_leaves(size_t num_trees, size_t leaves_per_tree, uint64_t seed = 0);
+}  // namespace CudaMerkleUtils
+
+}  // namespace MerkleTreeCUDA
+}  // namespace MerkleTree

@@ -65,6 +65,7 @@ _SIGS = {
     "cuzk_shutdown": (C.c_int, []),
     "cuzk_is_initialized": (C.c_int, []),
     "cuzk_device_count": (C.c_int, []),
+    "cuzk_device_info": (C.c_int, [C.c_int, C.c_void_p]),
     "cuzk_last_error": (C.c_char_p, []),
     "cuzk_version": (C.c_char_p, []),
     "cuzk_launch_count": (C.c_uint64, []),

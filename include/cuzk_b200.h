@@ -54,6 +54,16 @@ int cuzk_init(int device);
 int cuzk_shutdown(void);
 int cuzk_is_initialized(void);
 int cuzk_device_count(void); /* CudaFieldArithmetic::get_device_count (field_arithmetic_cuda.cuh:60) */
+/* device properties for CudaFieldArithmetic::print_device_info (field_arithmetic_cuda.cu:633-645) and
+ * CudaMerkleUtils::check_cuda_compatibility (merkle_tree_cuda.cu:596-616), so host code needs no CUDA runtime */
+typedef struct cuzk_device_info {
+  char name[256];
+  int cc_major, cc_minor;
+  int sm_count;
+  int max_threads_per_block;
+  size_t total_mem_bytes;
+} cuzk_device_info_t;
+int cuzk_device_info(int device, cuzk_device_info_t *out);
 const char *cuzk_last_error(void);
 const char *cuzk_version(void);
 /* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */

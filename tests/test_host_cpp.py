@@ -1,0 +1,96 @@
+"""The C++ host layer (cuzk_b200/host): the reference's CUDA-side classes over the C ABI.
+
+CPU part: the library builds with plain g++ and exports the reference's class names.
+GPU part: (1) tests/cpp/test_host_layer -- our C++ parity suite against the plain-C oracle;
+(2) oracle/_ref/bin/test_*_cuda -- the REFERENCE'S OWN GPU test sources, compiled unmodified against our host
+layer and its own CPU implementation by oracle/build_reference_tests.sh (prebuilt in the build container; the
+reference tree does not exist on the GPU box).
+"""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST_SO = os.path.join(ROOT, "cuzk_b200", "host", "libcuzk_host.so")
+HOST_TEST = os.path.join(ROOT, "tests", "cpp", "test_host_layer")
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "bin")
+
+
+def _build():
+    from cuzk_b200 import lib
+
+    lib.build_library()
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "liboracle"])
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "cuzk_b200", "host")])
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp")])
+
+
+def test_host_library_exports_reference_class_names():
+    _build()
+    syms = subprocess.check_output(["nm", "-DC", "--defined-only", HOST_SO], text=True)
+    for want in (
+        "Poseidon::PoseidonCUDA::CudaPoseidonHash::batch_hash_pairs(",
+        "Poseidon::PoseidonCUDA::CudaPoseidonHash::batch_hash_single(",
+        "Poseidon::PoseidonCUDA::CudaPoseidonHash::batch_permutation(",
+        "Poseidon::CudaFieldOps::CudaFieldArithmetic::batch_multiply(",
+        "Poseidon::CudaFieldOps::CudaFieldArithmetic::initialize()",
+        "MerkleTree::MerkleTreeCUDA::CudaNaryMerkleTree::build_tree(",
+        "MerkleTree::MerkleTreeCUDA::CudaNaryMerkleTree::verify_batch_proofs(",
+        "MerkleTree::MerkleTreeCUDA::CudaNaryMerkleTree::generate_proof(",
+        "MerkleTree::MerkleTreeCUDA::benchmark_cuda_tree_building(",
+        "Poseidon::PoseidonCUDA::verify_cuda_implementations_match(",
+    ):
+        assert want in syms, f"{want} not exported by libcuzk_host.so"
+    # the host layer reaches the GPU only through the C ABI: no CUDA runtime, no oracle
+    undefined = subprocess.check_output(["nm", "-D", "--undefined-only", HOST_SO], text=True)
+    assert "cuzk_poseidon_hash_pairs" in undefined and "cuzk_merkle_build" in undefined
+    assert "cuda" not in undefined.lower().replace("cudafield", "").replace("cudaposeidon", "").replace("cudanary", "")
+    assert "cuzk_oracle" not in undefined
+
+
+def test_host_sources_have_no_cpu_arithmetic():
+    """No CPU fallback: the host layer never multiplies field elements or hashes on the CPU."""
+    src = os.path.join(ROOT, "cuzk_b200", "host", "src")
+    for dirpath, _, files in os.walk(src):
+        for f in files:
+            text = open(os.path.join(dirpath, f)).read()
+            code = re.sub(r"//.*", "", text)
+            assert "__int128" not in code or f == "field_element.cpp", f  # only to_dec's long division
+            assert "hash_multiple(" not in code and "FieldArithmetic::multiply" not in code, f
+            assert "oracle" not in code.lower(), f
+
+
+def test_host_test_binary_lists_tests():
+    _build()
+    out = subprocess.check_output([HOST_TEST, "--gtest_list_tests"], text=True)
+    assert "HostMerkle.EveryLevelEqualsOracle" in out and "HostPoseidon.SingleAndPairHashesEqualOracle" in out
+
+
+def _run_gtest(path, timeout=900):
+    res = subprocess.run([path], capture_output=True, text=True, timeout=timeout)
+    tail = res.stdout[-4000:] + res.stderr[-2000:]
+    assert res.returncode == 0, tail
+    m = re.search(r"\[  PASSED  \] (\d+) tests", res.stdout)
+    assert m and int(m.group(1)) > 0, tail
+    assert "[  FAILED  ]" not in res.stdout, tail
+    skipped = re.search(r"\[  SKIPPED \] (\d+) tests", res.stdout)
+    assert not skipped, "GPU tests were skipped on a GPU box:\n" + tail
+    return int(m.group(1))
+
+
+@pytest.mark.gpu
+def test_host_layer_cpp_suite_on_gpu():
+    assert os.path.exists(HOST_TEST), "tests/cpp/test_host_layer missing: run __graft_entry__.build()"
+    assert _run_gtest(HOST_TEST) >= 14
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,min_tests", [("test_field_arithmetic_cuda", 8), ("test_poseidon_cuda", 8),
+                                            ("test_merkle_tree_cuda", 15), ("test_merkle_benchmark_cuda", 6)])
+def test_reference_gpu_suites_pass_unmodified(name, min_tests):
+    path = os.path.join(REF_BIN, name)
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/bin not prebuilt (needs /root/reference at build time)")
+    assert _run_gtest(path, timeout=1500) >= min_tests
