@@ -7,7 +7,7 @@
  *
  * Parity is PINNED: oracle/Makefile also compiles the reference's own CPU sources
  * (unmodified, from /root/reference) into oracle/_ref/libcuzk_ref.so, and
- * tests/test_oracle_vs_ref.py + tests/golden/ (generated from that library by
+ * tests/test_oracle.py (test_oracle_vs_reference_*) + tests/golden/ (generated from that library by
  * tests/golden/generate_golden.py) check every function below against it.
  *
  * Each function cites the reference file:line whose behaviour it restates.
