@@ -157,11 +157,18 @@ class ClockSampler:
         while not self._stop.is_set():
             try:
                 sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
-                    else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                self.samples.append((time.perf_counter(), sm, rs))
-            except Exception:
-                pass
+            except Exception as e:  # noqa: BLE001
+                self.err = f"clock: {e}"
+                time.sleep(self.period)
+                continue
+            rs = 0
+            for fn in ("nvmlDeviceGetCurrentClocksEventReasons", "nvmlDeviceGetCurrentClocksThrottleReasons"):
+                try:
+                    rs = int(getattr(nv, fn)(self.h))
+                    break
+                except Exception as e:  # noqa: BLE001
+                    self.err = f"{fn}: {e}"
+            self.samples.append((time.perf_counter(), sm, rs))
             time.sleep(self.period)
 
     def stop(self):
@@ -172,7 +179,8 @@ class ClockSampler:
     def summary(self, t0, t1):
         sel = [(sm, rs) for t, sm, rs in self.samples if t0 <= t <= t1]
         if not sel:
-            return {"sm_mhz": None, "sm_max_mhz": getattr(self, "max_sm", None), "reasons": [], "samples": 0}
+            return {"sm_mhz": None, "sm_max_mhz": getattr(self, "max_sm", None), "reasons": [], "samples": 0,
+                    "error": getattr(self, "err", None), "total_samples": len(self.samples)}
         reasons = sorted({name for _, rs in sel for name, bit in self.REASONS if rs & bit})
         return {"sm_mhz": float(np.median([sm for sm, _ in sel])), "sm_max_mhz": self.max_sm, "reasons": reasons, "samples": len(sel)}
 
@@ -407,8 +415,10 @@ def main():
                     "api": "cuzk_poseidon_hash_pairs(mem=CUZK_MEM_HOST) on pinned host buffers", "steps": e2e_steps, "checked": e2e_ok,
                     "reference_harness_batch4096": {"value": b4096_value, "unit": UNIT, "calls": -(-n // b)}},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "imad", "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "T multiply-adds/s (32x32->64)",
-                         "frac": achieved / imad_peak, "traffic": None,
+            "roofline": {"bound": "imad", "kernel": "hash_pairs_kernel", "achieved": achieved / 1e12, "peak": imad_peak / 1e12,
+                         "unit": "T multiply-adds/s (32x32->64)", "frac": achieved / imad_peak, "traffic": ncu_traffic(),
+                         "algorithmic_bytes_per_launch": BYTES_PER_PAIR_HASH * n, "algorithmic_imad_per_launch": IMAD_PER_PERM * n,
+                         "kernel_ms_per_launch": ms_per_step,
                          "peak_source": "measured in this run by cuzk_imad_peak (IMAD.WIDE.U32 microbenchmark, whole chip)",
                          "imad_per_hash": IMAD_PER_PERM, "pipe_microbench_per_s": peak,
                          "hbm": {"achieved_gbs": value / world * BYTES_PER_PAIR_HASH / 1e9, "peak_gbs": measured_hbm(),
@@ -420,6 +430,16 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per hash_pairs_kernel launch (1M pairs), taken from the committed
+    `ncu --set full` capture (profiles/hash_pairs_traffic.json, written by tools/ncu_summary.py); None when absent."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "hash_pairs_traffic.json")))
+        return {"bytes_per_launch": t["dram_bytes_read"] + t["dram_bytes_write"], "source": t["source"]}
+    except Exception:
+        return None
 
 
 def measured_hbm():

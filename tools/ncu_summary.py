@@ -36,4 +36,18 @@ with open(out, "w") as f:
     tot = sum(v for v, _ in items) or 1
     for v, h in sorted(items, reverse=True)[:10]:
         f.write(f"{h.replace('smsp__pcsamp_warps_issue_stalled_', ''):30s} {v / tot:6.1%}\n")
+def _num(key):
+    if key not in hdr:
+        return None
+    i = hdr.index(key)
+    v = float(data[0][i].replace(",", ""))
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[i], 1)
+    return v * scale
+
+
+if len(sys.argv) > 3:  # also write the per-launch DRAM traffic bench.py reports as roofline.traffic
+    import json
+
+    json.dump({"dram_bytes_read": _num("dram__bytes_read.sum"), "dram_bytes_write": _num("dram__bytes_write.sum"),
+               "source": out}, open(sys.argv[3], "w"))
 print(open(out).read())
