@@ -191,6 +191,9 @@ def main():
     if args.impl == "reference":
         reference_arm(args)
         return
+    # keep stdout clean for the ONE JSON line: libraries (NCCL prints its version banner) write to fd 1 otherwise
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -427,7 +430,8 @@ def main():
             "clocks": clocks,
             "merkle": merkle,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -292,3 +292,106 @@ def test_mds_layer_fast_path_and_fallback(gpu, oracle):
         got = to_host(d).reshape(-1, 3, 4)
         bad = np.nonzero((got != want).any(axis=(1, 2)))[0]
         assert bad.size == 0, (mode, bad[:4], hexes(st[bad[0]]) if bad.size else None)
+
+
+# ------------------------------------------------------- BASELINE full sizes, size-independent properties ----
+def _level_views(flat, n, arity):
+    out, off, p = [], 0, 1
+    while p < n:
+        p *= arity
+    while True:
+        out.append(flat[off : off + p])
+        off += p
+        if p == 1:
+            return out
+        p //= arity
+
+
+def _check_sampled_nodes(levels, arity, oracle, rng, per_level=48):
+    """chain of custody: sampled nodes of every level == oracle hash_multiple of OUR children one level below"""
+    for l in range(1, len(levels)):
+        m = levels[l].shape[0]
+        sel = np.unique(np.r_[0, m - 1, rng.integers(0, m, size=min(m, per_level))])
+        kids = to_host(levels[l - 1].reshape(m, arity, 4)[sel.tolist()].reshape(-1, 4))
+        got = to_host(levels[l][sel.tolist()])
+        assert (got == oracle.sponge(kids, arity, 3)).all(), l
+
+
+def test_config3_quaternary_2p20_full_batch_verify(gpu, oracle):
+    """BASELINE configs[2]: 4-ary tree over 2^20 leaves with full-batch proof verification (device resident)."""
+    import torch
+
+    from cuzk_b200 import lib
+
+    L = lib.get_lib()
+    n, arity = 1 << 20, 4
+    leaves = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+    L.check(L.cuzk_synth_u64_leaves(leaves.data_ptr(), n, 3, 0, None), "synth")
+    assert (to_host(leaves[:64]) == synth_u64_leaves(3, 64)).all()
+    t = gpu.CudaNaryMerkleTree(leaves, arity=arity)
+    levels = t.get_tree_levels()
+    assert len(levels) == 11 and levels[0].shape[0] == n
+    rng = np.random.default_rng(3)
+    _check_sampled_nodes(levels, arity, oracle, rng)
+    idx = torch.arange(n, dtype=torch.int64, device="cuda")
+    pb = t.generate_batch_proofs(idx)
+    assert tuple(pb.siblings.shape) == (n, 10, 3, 4)
+    res = t.verify_batch_proofs(pb, leaves)
+    assert bool(res.all()), "a valid proof of the full batch was rejected"
+    # every proof path of a sample equals the oracle's walk over OUR level arrays
+    host_levels = None
+    for q in rng.integers(0, n, size=8).tolist():
+        at = q
+        for l in range(10):
+            grp = to_host(levels[l][at - at % arity : at - at % arity + arity])
+            assert int(pb.positions[q, l]) == at % arity
+            assert (to_host(pb.siblings[q, l]) == np.delete(grp, at % arity, axis=0)).all()
+            at //= arity
+    # corrupt a known subset: exactly those proofs fail
+    bad = np.unique(rng.integers(0, n, size=1000))
+    lv = leaves.clone()
+    lv[bad.tolist(), 0] ^= 1
+    res2 = t.verify_batch_proofs(pb, lv).cpu().numpy()
+    want = np.ones(n, dtype=np.uint8)
+    want[bad] = 0
+    assert (res2 == want).all()
+    del pb, lv
+
+
+def test_config4_octary_2p26_sharded_equals_full_build(gpu, oracle):
+    """BASELINE configs[3]: 8-ary tree over 2^26 leaves.  Full build (every level kept) and the sharded subtree-root
+    decomposition for world sizes 1/2/4/8 (run shard by shard on this GPU) must give one and the same root, and sampled
+    nodes must equal the oracle's hash of their children."""
+    import torch
+
+    from cuzk_b200 import lib
+    from cuzk_b200.distributed import plan_merkle_shards
+
+    L = lib.get_lib()
+    n, arity = 1 << 26, 8
+    leaves = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+    L.check(L.cuzk_synth_u64_leaves(leaves.data_ptr(), n, 4, 0, None), "synth")
+    t = gpu.CudaNaryMerkleTree(leaves, arity=arity)
+    levels = t.get_tree_levels()
+    assert len(levels) == 10 and levels[0].shape[0] == 1 << 27     # padded to 8^9
+    assert t.get_tree_height() == 10                               # float formula agrees here (2^26 is not a power of 8)
+    _check_sampled_nodes(levels, arity, oracle, np.random.default_rng(4), per_level=24)
+    # padding: the upper half of every level is the level's padding constant
+    for l in (0, 3, 8):
+        assert (to_host(levels[l][-1:]) == gpu.padding_root(arity, l)).all()
+    root = to_host(levels[-1])[0]
+    del t, levels
+    torch.cuda.empty_cache()
+    for world in (1, 2, 4, 8):
+        plan = plan_merkle_shards(n, arity, world)
+        nodes = torch.empty((plan.total_subtrees, 4), dtype=torch.int64, device="cuda")
+        for rank in range(world):
+            lo, hi = plan.rank_subtrees(rank)
+            l0, l1 = plan.rank_leaves(rank)
+            L.check(L.cuzk_merkle_subtree_roots(leaves[l0:l1].data_ptr(), l1 - l0, arity, plan.height, hi - lo,
+                                                nodes[lo:hi].data_ptr(), 0, None), "subtree_roots")
+        if plan.total_subtrees > plan.real_subtrees:
+            nodes[plan.real_subtrees :] = to_dev(gpu.padding_root(arity, plan.height).reshape(1, 4))
+        out = torch.empty((1, 4), dtype=torch.int64, device="cuda")
+        L.check(L.cuzk_merkle_top_root(nodes.data_ptr(), plan.total_subtrees, arity, out.data_ptr(), 0, None), "top_root")
+        assert (to_host(out)[0] == root).all(), world
