@@ -239,6 +239,24 @@ def padding_root(arity: int, height: int) -> np.ndarray:
     return out
 
 
+def build_batch_trees(batch_leaves, arity: int = 2):
+    """CudaNaryMerkleTree::build_batch_trees for equal-sized trees: ``batch_leaves`` is (T, n, 4); returns T trees built by
+    one forest pass (cuzk_merkle_build_batch)."""
+    x = _elems(batch_leaves)
+    T = int(batch_leaves.shape[0])
+    n = x.shape[0] // T
+    lib = get_lib()
+    tot = total_nodes(n, arity)
+    out = _empty_like(x, tot * T)
+    lib.check(lib.cuzk_merkle_build_batch(_ptr(x), n, T, arity, _ptr(out), _mem(x), _stream(x)), "cuzk_merkle_build_batch")
+    trees = []
+    for t in range(T):
+        tree = CudaNaryMerkleTree(arity=arity)
+        tree.leaf_count, tree.levels = n, out[t * tot : (t + 1) * tot]
+        trees.append(tree)
+    return trees
+
+
 class MerkleProofBatch:
     """Flat, level-uniform proof batch: siblings (q, L, arity-1, 4), positions (q, L) uint32, leaf indices (q,)."""
 

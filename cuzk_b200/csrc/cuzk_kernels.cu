@@ -222,14 +222,17 @@ __global__ void padding_chain_kernel(uint4 *pad, int arity, int levels) {
   }
 }
 
-// level 0: copy the n leaves and append padding E_0 up to `padded`
+// level 0: copy the n leaves and append padding E_0 up to `padded`.  Forest form: tree t reads leaves + t * n and writes
+// out + t * out_stride (elements); a single tree is ntrees = 1.
 __global__ void merkle_pad_leaves_kernel(const uint4 *__restrict__ leaves, size_t n, size_t padded,
-                                         const uint4 *__restrict__ pad, uint4 *__restrict__ out) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= padded) return;
-  const uint4 *src = (i < n) ? (leaves + 2 * i) : pad;
-  out[2 * i] = src[0];
-  out[2 * i + 1] = src[1];
+                                         const uint4 *__restrict__ pad, uint4 *__restrict__ out, size_t ntrees, size_t out_stride) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= padded * ntrees) return;
+  const size_t tree = t / padded, i = t - tree * padded;
+  const uint4 *src = (i < n) ? (leaves + 2 * (tree * n + i)) : pad;
+  uint4 *dst = out + 2 * (tree * out_stride + i);
+  dst[0] = src[0];
+  dst[1] = src[1];
 }
 
 // one level: out[i] = hash_multiple(in[i*arity .. i*arity+arity-1]).  Only the first `in_real` inputs exist in
@@ -238,9 +241,14 @@ __global__ void merkle_pad_leaves_kernel(const uint4 *__restrict__ leaves, size_
 // build_level_kernel : merkle_tree_cuda.cu:45-64 / build_tree_bottom_up : merkle_tree.cpp:66-97
 __global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) merkle_level_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out,
                                                                size_t in_real, size_t out_count, int arity,
-                                                               const uint4 *__restrict__ pad_in, const uint4 *__restrict__ pad_out) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= out_count) return;
+                                                               const uint4 *__restrict__ pad_in, const uint4 *__restrict__ pad_out,
+                                                               size_t ntrees, size_t tree_stride) {
+  // forest form: `ntrees` trees of identical shape, tree t at in/out + t * tree_stride elements; thread = (tree, node)
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= out_count * ntrees) return;
+  const size_t tree = t / out_count, i = t - tree * out_count;
+  in += 2 * tree * tree_stride;
+  out += 2 * tree * tree_stride;
   const size_t first = i * (size_t)arity;
   if (first >= in_real) {
     out[2 * i] = pad_out[0];
@@ -260,10 +268,15 @@ __global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) merkle_level_kernel(c
 // Same padding rules as merkle_level_kernel (pad_in / pad_mid / pad_out are consecutive padding constants).
 __global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) merkle_fused2_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ mid_out,
                                                                 uint4 *__restrict__ out, size_t in_real, size_t out_count,
-                                                                int arity, const uint4 *__restrict__ pad) {
+                                                                int arity, const uint4 *__restrict__ pad, size_t ntrees,
+                                                                size_t tree_stride) {
   extern __shared__ uint4 smem[];                    // [2 * arity][kBlock] uint4: slot-major, so a warp's accesses never conflict
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= out_count) return;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= out_count * ntrees) return;
+  const size_t tree = t / out_count, i = t - tree * out_count;   // forest form, see merkle_level_kernel
+  in += 2 * tree * tree_stride;
+  out += 2 * tree * tree_stride;
+  if (mid_out) mid_out += 2 * tree * tree_stride;
   const uint4 *pad_in = pad, *pad_mid = pad + 2, *pad_out = pad + 4;
   const size_t span = (size_t)arity * arity;
   if (i * span >= in_real) {
@@ -559,39 +572,46 @@ int fr_batch_dev(int op, const uint64_t *a, const uint64_t *b, uint64_t *out, si
 // per level so that each node keeps its own thread (a fused thread hashes arity + 1 nodes back to back).
 constexpr size_t kFuseMinOut = 148 * 7 * 128;
 
-int launch_level(const uint4 *in, uint4 *out, size_t in_real, size_t out_count, unsigned arity, const uint4 *pad_in, cudaStream_t st) {
-  merkle_level_kernel<<<grid_for(out_count, kBlock), kBlock, 0, st>>>(in, out, in_real, out_count, (int)arity, pad_in, pad_in + 2);
+int launch_level(const uint4 *in, uint4 *out, size_t in_real, size_t out_count, unsigned arity, const uint4 *pad_in, cudaStream_t st,
+                 size_t ntrees = 1, size_t tree_stride = 0) {
+  merkle_level_kernel<<<grid_for(out_count * ntrees, kBlock), kBlock, 0, st>>>(in, out, in_real, out_count, (int)arity, pad_in, pad_in + 2,
+                                                                               ntrees, tree_stride);
   return check_launch("merkle_level_kernel");
 }
 int launch_fused2(const uint4 *in, uint4 *mid, uint4 *out, size_t in_real, size_t out_count, unsigned arity, const uint4 *pad_in,
-                  cudaStream_t st) {
+                  cudaStream_t st, size_t ntrees = 1, size_t tree_stride = 0) {
   const size_t smem = (size_t)2 * arity * kBlock * sizeof(uint4);
-  merkle_fused2_kernel<<<grid_for(out_count, kBlock), kBlock, smem, st>>>(in, mid, out, in_real, out_count, (int)arity, pad_in);
+  merkle_fused2_kernel<<<grid_for(out_count * ntrees, kBlock), kBlock, smem, st>>>(in, mid, out, in_real, out_count, (int)arity, pad_in,
+                                                                                   ntrees, tree_stride);
   return check_launch("merkle_fused2_kernel");
 }
 
-int merkle_build_dev(const uint64_t *leaves, size_t n, unsigned arity, uint64_t *levels_out, cudaStream_t st) {
+// builds `ntrees` trees of n leaves each in one pass: one launch per level (or per two levels) for the whole forest.
+// leaves: ntrees x n elements; levels_out: ntrees flat level-major trees of total_nodes(n) elements each.
+int merkle_build_dev(const uint64_t *leaves, size_t n, unsigned arity, uint64_t *levels_out, cudaStream_t st, size_t ntrees = 1) {
   int rc = ensure_padding(arity);
   if (rc) return rc;
   const uint4 *pad = reinterpret_cast<const uint4 *>(g_d_pad[arity]);
   size_t padded = cuzk_merkle_padded_leaves(n, arity);
   if ((int)cuzk_merkle_num_levels(n, arity) >= g_pad_levels[arity]) return fail(CUZK_ERR_INVALID, "tree too tall");
+  const size_t stride = cuzk_merkle_total_nodes(n, arity);
   uint4 *cur = reinterpret_cast<uint4 *>(levels_out);
-  merkle_pad_leaves_kernel<<<grid_for(padded, 256), 256, 0, st>>>(reinterpret_cast<const uint4 *>(leaves), n, padded, pad, cur);
+  merkle_pad_leaves_kernel<<<grid_for(padded * ntrees, 256), 256, 0, st>>>(reinterpret_cast<const uint4 *>(leaves), n, padded, pad, cur,
+                                                                          ntrees, stride);
   if ((rc = check_launch("merkle_pad_leaves_kernel"))) return rc;
   size_t p = padded, real = n;
   int level = 0;
   while (p > 1) {
     const size_t q = p / arity;
-    if (q > 1 && q / arity >= kFuseMinOut) {
+    if (q > 1 && (q / arity) * ntrees >= kFuseMinOut) {
       const size_t q2 = q / arity;
-      if ((rc = launch_fused2(cur, cur + 2 * p, cur + 2 * p + 2 * q, real, q2, arity, pad + 2 * level, st))) return rc;
+      if ((rc = launch_fused2(cur, cur + 2 * p, cur + 2 * p + 2 * q, real, q2, arity, pad + 2 * level, st, ntrees, stride))) return rc;
       cur += 2 * p + 2 * q;
       real = ceil_div(ceil_div(real, arity), arity);
       p = q2;
       level += 2;
     } else {
-      if ((rc = launch_level(cur, cur + 2 * p, real, q, arity, pad + 2 * level, st))) return rc;
+      if ((rc = launch_level(cur, cur + 2 * p, real, q, arity, pad + 2 * level, st, ntrees, stride))) return rc;
       cur += 2 * p;
       real = ceil_div(real, arity);
       p = q;
@@ -610,7 +630,7 @@ int subtree_roots_dev(const uint64_t *leaves, size_t n, unsigned arity, unsigned
   const uint4 *pad = reinterpret_cast<const uint4 *>(g_d_pad[arity]);
   if (height == 0) {
     merkle_pad_leaves_kernel<<<grid_for(count, 256), 256, 0, st>>>(reinterpret_cast<const uint4 *>(leaves), n, count, pad,
-                                                                  reinterpret_cast<uint4 *>(roots_out));
+                                                                  reinterpret_cast<uint4 *>(roots_out), 1, 0);
     return check_launch("merkle_pad_leaves_kernel");
   }
   // stream-ordered scratch for the levels between the leaves and the roots; only nodes with a real leaf below them are stored
@@ -905,6 +925,28 @@ int cuzk_merkle_build(const uint64_t *leaves, size_t n, unsigned arity, uint64_t
   if ((rc = ws_get(0, n * 32, &dl)) || (rc = ws_get(1, tot * 32, &dv))) return rc;
   CK(cudaMemcpyAsync(dl, leaves, n * 32, cudaMemcpyHostToDevice, st));
   rc = merkle_build_dev(static_cast<uint64_t *>(dl), n, arity, static_cast<uint64_t *>(dv), st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(levels_out, dv, tot * 32, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return CUZK_OK;
+}
+
+int cuzk_merkle_build_batch(const uint64_t *leaves, size_t n, size_t num_trees, unsigned arity, uint64_t *levels_out, int mem,
+                            void *stream) {
+  int rc = require_init();
+  if (rc) return rc;
+  if ((rc = check_arity(arity))) return rc;
+  if (num_trees == 0) return CUZK_OK;
+  if (n == 0) return fail(CUZK_ERR_INVALID, "cuzk_merkle_build_batch: n must be >= 1");
+  if (!leaves || !levels_out) return fail(CUZK_ERR_INVALID, "null pointer");
+  cudaStream_t st = S(stream);
+  if (mem == CUZK_MEM_DEVICE) return merkle_build_dev(leaves, n, arity, levels_out, st, num_trees);
+  std::lock_guard<std::mutex> lk(g_hp_mu);
+  const size_t tot = cuzk_merkle_total_nodes(n, arity) * num_trees;
+  void *dl, *dv;
+  if ((rc = ws_get(0, n * num_trees * 32, &dl)) || (rc = ws_get(1, tot * 32, &dv))) return rc;
+  CK(cudaMemcpyAsync(dl, leaves, n * num_trees * 32, cudaMemcpyHostToDevice, st));
+  rc = merkle_build_dev(static_cast<uint64_t *>(dl), n, arity, static_cast<uint64_t *>(dv), st, num_trees);
   if (rc) return rc;
   CK(cudaMemcpyAsync(levels_out, dv, tot * 32, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));

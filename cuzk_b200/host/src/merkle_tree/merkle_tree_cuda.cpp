@@ -66,18 +66,26 @@ bool CudaNaryMerkleTree::build_tree(const std::vector<FieldElement> &leaves) {
     leaves_.clear();
     return false;
   }
+  adopt_levels(leaves, flat.data());
+  return true;
+}
+
+// takes over the flat level-major array the library produced for `leaves` (level 0 = padded leaves, last = root)
+void CudaNaryMerkleTree::adopt_levels(const std::vector<FieldElement> &leaves, const FieldElement *flat) {
+  const unsigned arity = (unsigned)config_.arity;
+  const size_t n = leaves.size();
   leaves_ = leaves;
   leaf_count_ = n;
   tree_height_ = cuzk_merkle_tree_height(n, arity);  // the reference's float formula: a getter value only
   const size_t nlevels = cuzk_merkle_num_levels(n, arity);
+  tree_levels_.clear();
   tree_levels_.reserve(nlevels);
   size_t width = cuzk_merkle_padded_leaves(n, arity), at = 0;
   for (size_t l = 0; l < nlevels; ++l) {
-    tree_levels_.emplace_back(flat.begin() + at, flat.begin() + at + width);
+    tree_levels_.emplace_back(flat + at, flat + at + width);
     at += width;
     width /= arity;
   }
-  return true;
 }
 
 std::optional<MerkleProof> CudaNaryMerkleTree::generate_proof(size_t leaf_index) const {
@@ -163,10 +171,32 @@ bool CudaNaryMerkleTree::build_batch_trees(const std::vector<std::vector<FieldEl
                                            const MerkleTreeConfig &config) {
   trees.clear();
   trees.reserve(batch_leaves.size());
-  for (const auto &leaves : batch_leaves) {
-    CudaNaryMerkleTree tree(config);
-    if (!tree.build_tree(leaves)) return false;
-    trees.push_back(std::move(tree));
+  if (batch_leaves.empty()) return true;
+  const size_t n = batch_leaves[0].size();
+  bool uniform = n > 0;
+  for (const auto &leaves : batch_leaves) uniform = uniform && leaves.size() == n;
+  if (!uniform) {  // ragged batch: one build per tree, like the reference's loop (merkle_tree_cuda.cu:467-482)
+    for (const auto &leaves : batch_leaves) {
+      CudaNaryMerkleTree tree(config);
+      if (!tree.build_tree(leaves)) return false;
+      trees.push_back(std::move(tree));
+    }
+    return true;
+  }
+  // equal-sized trees: the whole forest is built by one pass of level launches (cuzk_merkle_build_batch)
+  if (!ensure_library()) return false;
+  const size_t count = batch_leaves.size(), per_tree = cuzk_merkle_total_nodes(n, (unsigned)config.arity);
+  std::vector<FieldElement> all_leaves;
+  all_leaves.reserve(count * n);
+  for (const auto &leaves : batch_leaves) all_leaves.insert(all_leaves.end(), leaves.begin(), leaves.end());
+  std::vector<FieldElement> flat(count * per_tree);
+  if (cuzk_merkle_build_batch(raw(all_leaves), n, count, (unsigned)config.arity, raw(flat), CUZK_MEM_HOST, nullptr) != CUZK_OK) {
+    std::cerr << "CudaNaryMerkleTree::build_batch_trees: " << cuzk_last_error() << std::endl;
+    return false;
+  }
+  for (size_t t = 0; t < count; ++t) {
+    trees.emplace_back(config);
+    trees.back().adopt_levels(batch_leaves[t], flat.data() + t * per_tree);
   }
   return true;
 }

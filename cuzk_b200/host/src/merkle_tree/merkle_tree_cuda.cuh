@@ -38,6 +38,7 @@ private:
   size_t tree_height_;
 
   FieldElement compute_empty_hash(size_t arity) const;
+  void adopt_levels(const std::vector<FieldElement> &leaves, const FieldElement *flat_levels);
 
 public:
   explicit CudaNaryMerkleTree(const MerkleTreeConfig &config = MerkleTreeConfig());

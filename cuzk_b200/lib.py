@@ -81,6 +81,7 @@ _SIGS = {
     "cuzk_merkle_tree_height": (C.c_size_t, [C.c_size_t, C.c_uint]),
     "cuzk_merkle_empty_hash": (C.c_int, [C.c_uint, C.c_void_p]),
     "cuzk_merkle_build": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_int, C.c_void_p]),
+    "cuzk_merkle_build_batch": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint, C.c_void_p, C.c_int, C.c_void_p]),
     "cuzk_merkle_subtree_roots": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint, C.c_uint, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]),
     "cuzk_merkle_top_root": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_int, C.c_void_p]),
     "cuzk_merkle_padding_root": (C.c_int, [C.c_uint, C.c_uint, C.c_void_p]),

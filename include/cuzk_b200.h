@@ -109,6 +109,13 @@ int cuzk_merkle_empty_hash(unsigned arity, uint64_t out[4]);
 int cuzk_merkle_build(const uint64_t *leaves, size_t n, unsigned arity, uint64_t *levels_out, int mem,
                       void *stream);
 
+/* CudaNaryMerkleTree::build_batch_trees (merkle_tree_cuda.cuh:79-81; a serial loop of full builds in the reference,
+ * merkle_tree_cuda.cu:467-482) for `num_trees` trees of `n` leaves each as ONE forest pass: one launch per level (or per
+ * two levels) covers every tree.  leaves: num_trees x n elements, tree-major; levels_out: num_trees flat level-major
+ * trees of cuzk_merkle_total_nodes(n, arity) elements each, tree-major. */
+int cuzk_merkle_build_batch(const uint64_t *leaves, size_t n, size_t num_trees, unsigned arity, uint64_t *levels_out,
+                            int mem, void *stream);
+
 /* Subtree-root pass (the multi-GPU shard step, and the "only roots reach HBM" build): the `n` given leaves
  * are the first leaves of `count` consecutive subtrees of arity^height padded leaves each
  * (n <= count * arity^height; the tail is virtual padding).  roots_out[i] = root of subtree i, where

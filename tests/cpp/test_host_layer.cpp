@@ -367,6 +367,19 @@ TEST_F(HostMerkle, BatchTreesAndBenchmarkHelpers) {
   ASSERT_TRUE(CudaNaryMerkleTree::build_batch_trees(batch, trees, MerkleTreeConfig(4)));
   ASSERT_EQ(trees.size(), 10u);
   for (size_t t = 0; t < 10; ++t) EXPECT_EQ(trees[t].get_root_hash(), oracle_levels(batch[t], 4).back()[0]);
+  // ragged batch (falls back to one build per tree) and a larger uniform forest
+  std::vector<std::vector<FieldElement>> ragged{u64_leaves(5, 1), u64_leaves(64, 2), {}, u64_leaves(9, 3)};
+  ASSERT_TRUE(CudaNaryMerkleTree::build_batch_trees(ragged, trees, MerkleTreeConfig(2)));
+  ASSERT_EQ(trees.size(), 4u);
+  EXPECT_EQ(trees[1].get_root_hash(), oracle_levels(ragged[1], 2).back()[0]);
+  EXPECT_EQ(trees[2].get_leaf_count(), 0u);
+  const auto forest = CudaMerkleUtils::generate_batch_test_leaves(50, 2048, 777);
+  ASSERT_TRUE(CudaNaryMerkleTree::build_batch_trees(forest, trees, MerkleTreeConfig(8)));
+  for (size_t t : {size_t(0), size_t(31), size_t(49)}) {
+    const auto want = oracle_levels(forest[t], 8);
+    ASSERT_EQ(trees[t].get_tree_levels().size(), want.size());
+    for (size_t l = 0; l < want.size(); ++l) EXPECT_TRUE(trees[t].get_tree_levels()[l] == want[l]);
+  }
   const CudaMerkleTreeStats b = benchmark_cuda_tree_building(4, 256, 4);
   EXPECT_GT(b.build_time_ms, 0.0);
   const CudaMerkleTreeStats v = benchmark_cuda_proof_verification(200, 256, 4);

@@ -273,6 +273,21 @@ def test_subtree_roots_and_top_equal_full_build(gpu, oracle):
             assert (to_host(roots[real:]) == gpu.padding_root(arity, height)).all()
 
 
+def test_forest_build_equals_per_tree_builds(gpu, oracle):
+    """cuzk_merkle_build_batch: many equal-sized trees in one forest pass == the oracle's tree, tree by tree."""
+    for arity, n, T in ((2, 32, 10), (4, 100, 7), (8, 2048, 5), (3, 1, 4), (8, 4096, 40)):
+        leaves = synth_u64_leaves(11, n * T).reshape(T, n, 4)
+        for dev in (False, True):
+            trees = gpu.build_batch_trees(to_dev(leaves.reshape(-1, 4)).reshape(T, n, 4) if dev else leaves, arity=arity)
+            assert len(trees) == T
+            for t in (0, T // 2, T - 1):
+                want = oracle.merkle_build(leaves[t], arity)
+                got = [to_host(x) if dev else x for x in trees[t].get_tree_levels()]
+                assert len(got) == len(want)
+                for gl, wl in zip(got, want):
+                    assert (gl == wl).all(), (arity, n, T, t, dev)
+
+
 def test_mds_layer_fast_path_and_fallback(gpu, oracle):
     """The fast MDS layer (linear form + wrap count + exact fallback) against the oracle's term-by-term layer, on
     states crafted to sit on every decision boundary, and against the GPU's own exact path."""
