@@ -69,7 +69,7 @@ inline unsigned grid_for(size_t n, unsigned block) {
 #define CUZK_BLOCK 128
 #endif
 #ifndef CUZK_MIN_BLOCKS
-#define CUZK_MIN_BLOCKS 7   // 72 registers: measured best on B200 (profiles/r01_tuning_notes.md)
+#define CUZK_MIN_BLOCKS 6   // 80 registers: measured best on B200 (profiles/r01_tuning_notes.md)
 #endif
 constexpr int kBlock = CUZK_BLOCK;
 
@@ -123,14 +123,9 @@ __global__ void __launch_bounds__(kBlock) fr_batch_kernel(const uint4 *__restric
 __global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) hash_single_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  u32 s0[8], s1[8], s2[8], x[8];
-  set_small(s0, 1);
-  set_small(s1, 0);
-  set_small(s2, 0);
-  load_fr(x, in + 2 * i);
-  absorb(s1, x);
-  permute<true>(s0, s1, s2);
-  store_fr(out + 2 * i, s1);
+  u32 r[8];
+  sponge_n(r, 1u, 1, [&](u32(&x)[8], int) { load_fr(x, in + 2 * i); });
+  store_fr(out + 2 * i, r);
 }
 
 // batch_hash_pairs: state [2, l, r]  -- the headline kernel
@@ -138,27 +133,30 @@ __global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) hash_pairs_kernel(con
                                                              uint4 *__restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  u32 s0[8], s1[8], s2[8], x[8];
-  set_small(s0, 2);
-  set_small(s1, 0);
-  set_small(s2, 0);
-  load_fr(x, l + 2 * i);
-  absorb(s1, x);
-  load_fr(x, r + 2 * i);
-  absorb(s2, x);
-  permute<true>(s0, s1, s2);
-  store_fr(out + 2 * i, s1);
+  u32 h[8];
+  sponge_n(h, 2u, 2, [&](u32(&x)[8], int j) { load_fr(x, (j == 0 ? l : r) + 2 * i); });
+  store_fr(out + 2 * i, h);
 }
 
 // batch_permutation: in-place, caller-supplied (possibly non-canonical) states
 __global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) permutation_kernel(uint4 *states, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  u32 s0[8], s1[8], s2[8];
+  u32 s0[8], s1[8], s2[8], unc = 0;
   load_fr_plain(s0, states + 6 * i);
   load_fr_plain(s1, states + 6 * i + 2);
   load_fr_plain(s2, states + 6 * i + 4);
-  permute<false>(s0, s1, s2);
+  permute_t<false, false>(s0, s1, s2, unc);
+  if (unc != 0) {   // undecided comparison on the fast path: evaluate again exactly from the untouched input
+    atomicAdd(&g_exact_fallbacks, 1ull);
+    u32 st[24];
+    const u32 *src = reinterpret_cast<const u32 *>(states + 6 * i);
+#pragma unroll
+    for (int w = 0; w < 24; ++w) st[w] = src[w];
+    permute_exact(st, 0);
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { s0[w] = st[w]; s1[w] = st[8 + w]; s2[w] = st[16 + w]; }
+  }
   store_fr(states + 6 * i, s0);
   store_fr(states + 6 * i + 2, s1);
   store_fr(states + 6 * i + 4, s2);
@@ -185,23 +183,9 @@ __global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) sponge_kernel(const u
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint4 *base = in + 2 * i * (size_t)width;
-  u32 s0[8], s1[8], s2[8];
-  set_small(s0, ds_lo);
-  s0[1] = ds_hi;
-  set_small(s1, 0);
-  set_small(s2, 0);
-#pragma unroll 1
-  for (int j = 0; j < width; j += 2) {
-    u32 x[8];
-    load_fr(x, base + 2 * j);
-    absorb(s1, x);
-    if (j + 1 < width) {
-      load_fr(x, base + 2 * (j + 1));
-      absorb(s2, x);
-    }
-    permute<true>(s0, s1, s2);
-  }
-  store_fr(out + 2 * i, s1);
+  u32 r[8];
+  sponge_n(r, ds_lo, ds_hi, width, [&](u32(&x)[8], int j) { load_fr(x, base + 2 * j); });
+  store_fr(out + 2 * i, r);
 }
 
 // padding chain for one arity: pad[0] = hash_multiple(arity zeros), pad[l+1] = hash_multiple(arity x pad[l])
@@ -426,7 +410,7 @@ namespace {
 // between two internal streams, so the H2D copy of chunk c+1 and the D2H copy of chunk c-1 overlap the kernel of chunk c.
 constexpr int kPipeStreams = 2;
 constexpr int kPipeSlots = 4;                       // up to 3 inputs + 1 output per stream
-constexpr size_t kHashChunk = 148 * 7 * 128;        // one resident wave of one-thread-per-hash CTAs
+constexpr size_t kHashChunk = 148 * CUZK_MIN_BLOCKS * CUZK_BLOCK;   // one resident wave of one-thread-per-hash CTAs
 constexpr size_t kCheapChunk = 1 << 20;             // element-wise field ops
 constexpr int kWsSlots = 6;
 
@@ -570,7 +554,7 @@ int fr_batch_dev(int op, const uint64_t *a, const uint64_t *b, uint64_t *out, si
 
 // Two levels are fused per launch while the upper of the two still fills the chip; narrower levels run one launch
 // per level so that each node keeps its own thread (a fused thread hashes arity + 1 nodes back to back).
-constexpr size_t kFuseMinOut = 148 * 7 * 128;
+constexpr size_t kFuseMinOut = 148 * CUZK_MIN_BLOCKS * CUZK_BLOCK;
 
 int launch_level(const uint4 *in, uint4 *out, size_t in_real, size_t out_count, unsigned arity, const uint4 *pad_in, cudaStream_t st,
                  size_t ntrees = 1, size_t tree_stride = 0) {
@@ -682,6 +666,11 @@ extern "C" {
 const char *cuzk_last_error(void) { return g_err.c_str(); }
 const char *cuzk_version(void) { return "cuzk_b200 0.2 (sm_100a)"; }
 uint64_t cuzk_launch_count(void) { return g_launches.load(); }
+uint64_t cuzk_debug_fallback_count(void) {
+  unsigned long long v = 0;
+  if (cudaMemcpyFromSymbol(&v, g_exact_fallbacks, sizeof v) != cudaSuccess) return ~0ull;
+  return v;
+}
 
 int cuzk_device_count(void) {
   int n = 0;

@@ -112,6 +112,71 @@ __device__ __forceinline__ void fr_reduce(u32 (&x)[8]) {
   cond_sub_mp<1>(x);
 }
 
+// ---- fast path: conditional subtract decided by the top word alone ------------------------------------------
+// x -= M*p when x[7] > top word of M*p, which proves x >= M*p; x[7] < top proves x < M*p.  The undecided case
+// x[7] == top (2^-32 per call on random data) is reported in `unc`: the caller then recomputes its whole unit (hash,
+// node, proof level) on the exact path, so results stay bit-exact.  One ISETP + eight predicated IADD3.X instead of
+// eight IADD3.X + eight SEL.  `enable` == 0 turns the subtraction off (used for the reference's "mh == 0" case).
+// CUZK_UNC_WIDEN > 0 (debug builds only) flags near-misses too, to exercise the exact fallback in tests.
+#ifndef CUZK_UNC_WIDEN
+#define CUZK_UNC_WIDEN 0
+#endif
+template <int M>
+__device__ __forceinline__ void cond_sub_top(u32 (&x)[8], u32 &unc, u32 enable) {
+  constexpr u32 T = mulp_limb(M, 7);
+  unc |= (((x[7] ^ T) >> CUZK_UNC_WIDEN) == 0u) ? 1u : 0u;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e, p;\n\t"
+      "setp.ne.u32 e, %16, 0;\n\t"
+      "setp.gt.and.u32 p, %7, %15, e;\n\t"
+      "@p sub.cc.u32 %0, %0, %8;\n\t"
+      "@p subc.cc.u32 %1, %1, %9;\n\t"
+      "@p subc.cc.u32 %2, %2, %10;\n\t"
+      "@p subc.cc.u32 %3, %3, %11;\n\t"
+      "@p subc.cc.u32 %4, %4, %12;\n\t"
+      "@p subc.cc.u32 %5, %5, %13;\n\t"
+      "@p subc.cc.u32 %6, %6, %14;\n\t"
+      "@p subc.u32 %7, %7, %15;\n\t"
+      "}"
+      : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7])
+      : "n"(mulp_limb(M, 0)), "n"(mulp_limb(M, 1)), "n"(mulp_limb(M, 2)), "n"(mulp_limb(M, 3)), "n"(mulp_limb(M, 4)),
+        "n"(mulp_limb(M, 5)), "n"(mulp_limb(M, 6)), "n"(mulp_limb(M, 7)), "r"(enable));
+}
+template <int M>
+__device__ __forceinline__ void cond_sub_top(u32 (&x)[8], u32 &unc) {
+  constexpr u32 T = mulp_limb(M, 7);
+  unc |= (((x[7] ^ T) >> CUZK_UNC_WIDEN) == 0u) ? 1u : 0u;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.gt.u32 p, %7, %15;\n\t"
+      "@p sub.cc.u32 %0, %0, %8;\n\t"
+      "@p subc.cc.u32 %1, %1, %9;\n\t"
+      "@p subc.cc.u32 %2, %2, %10;\n\t"
+      "@p subc.cc.u32 %3, %3, %11;\n\t"
+      "@p subc.cc.u32 %4, %4, %12;\n\t"
+      "@p subc.cc.u32 %5, %5, %13;\n\t"
+      "@p subc.cc.u32 %6, %6, %14;\n\t"
+      "@p subc.u32 %7, %7, %15;\n\t"
+      "}"
+      : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7])
+      : "n"(mulp_limb(M, 0)), "n"(mulp_limb(M, 1)), "n"(mulp_limb(M, 2)), "n"(mulp_limb(M, 3)), "n"(mulp_limb(M, 4)),
+        "n"(mulp_limb(M, 5)), "n"(mulp_limb(M, 6)), "n"(mulp_limb(M, 7)));
+}
+
+// reduce for ANY 256-bit x on the fast path (quotient <= 5: 4p, 2p, p ladder)
+__device__ __forceinline__ void fr_reduce_fast(u32 (&x)[8], u32 &unc) {
+  cond_sub_top<4>(x, unc);
+  cond_sub_top<2>(x, unc);
+  cond_sub_top<1>(x, unc);
+}
+__device__ __forceinline__ void fr_reduce_fast(u32 (&x)[8], u32 &unc, u32 enable) {
+  cond_sub_top<4>(x, unc, enable);
+  cond_sub_top<2>(x, unc, enable);
+  cond_sub_top<1>(x, unc, enable);
+}
+
 // add for canonical operands (a, b < p): sum < 2p < 2^256, at most one subtraction.
 __device__ __forceinline__ void fr_add_canon(u32 (&r)[8], const u32 (&a)[8], const u32 (&b)[8]) {
   r[0] = add_cc(a[0], b[0]);
@@ -244,7 +309,9 @@ __device__ __forceinline__ void mad_low_8x8(u32 (&t)[8], const u32 (&a)[8], cons
 // reduce_512 : field_arithmetic.cpp:250-330 on a 16-word product.
 //   Mh = high*k ; t = (Mh_lo + (Mh_hi*k mod W)) mod W ; hc = Mh_hi != 0 ? reduce(t) : t ;
 //   r = reduce((low + hc) mod W)
-__device__ __forceinline__ void fr_reduce_512(u32 (&r)[8], const u32 (&prod)[16]) {
+// EXACT = false uses the top-word reductions and reports undecided comparisons in `unc` (see cond_sub_top).
+template <bool EXACT>
+__device__ __forceinline__ void fr_reduce_512(u32 (&r)[8], const u32 (&prod)[16], u32 &unc) {
   const u32 kk[8] = {CUZK_K0, CUZK_K1, CUZK_K2, CUZK_K3, CUZK_K4, CUZK_K5, CUZK_K6, CUZK_K7};
   u32 high[8];
 #pragma unroll
@@ -256,19 +323,29 @@ __device__ __forceinline__ void fr_reduce_512(u32 (&r)[8], const u32 (&prod)[16]
 #pragma unroll
   for (int i = 0; i < 8; ++i) { t[i] = m1[i]; mh[i] = m1[8 + i]; mh_or |= m1[8 + i]; }
   mad_low_8x8(t, mh, kk);     // adds nothing when mh == 0, matching the reference's skip (:303)
-  if (mh_or != 0) fr_reduce(t);
+  if (EXACT) {
+    if (mh_or != 0) fr_reduce(t);
+  } else {
+    fr_reduce_fast(t, unc, mh_or);
+  }
   r[0] = add_cc(prod[0], t[0]);
 #pragma unroll
   for (int i = 1; i < 7; ++i) r[i] = addc_cc(prod[i], t[i]);
   r[7] = addc(prod[7], t[7]);
-  fr_reduce(r);
+  if (EXACT) fr_reduce(r);
+  else fr_reduce_fast(r, unc);
 }
 
 // multiply : field_arithmetic.cpp:221-238 (valid for arbitrary 256-bit operands)
-__device__ __forceinline__ void fr_mul(u32 (&r)[8], const u32 (&a)[8], const u32 (&b)[8]) {
+template <bool EXACT>
+__device__ __forceinline__ void fr_mul_t(u32 (&r)[8], const u32 (&a)[8], const u32 (&b)[8], u32 &unc) {
   u32 prod[16];
   mul_wide_8x8(prod, a, b);
-  fr_reduce_512(r, prod);
+  fr_reduce_512<EXACT>(r, prod, unc);
+}
+__device__ __forceinline__ void fr_mul(u32 (&r)[8], const u32 (&a)[8], const u32 (&b)[8]) {
+  u32 unused = 0;
+  fr_mul_t<true>(r, a, b, unused);
 }
 
 // r[0..15] = a * a using the symmetry of the product: the 28 off-diagonal products are accumulated once
@@ -322,18 +399,28 @@ __device__ __forceinline__ void sqr_wide_8(u32 (&r)[16], const u32 (&a)[8]) {
 }
 
 // square : field_arithmetic.cpp:240-242 (= multiply(a, a), evaluated with the symmetric product)
-__device__ __forceinline__ void fr_sqr(u32 (&r)[8], const u32 (&a)[8]) {
+template <bool EXACT>
+__device__ __forceinline__ void fr_sqr_t(u32 (&r)[8], const u32 (&a)[8], u32 &unc) {
   u32 prod[16];
   sqr_wide_8(prod, a);
-  fr_reduce_512(r, prod);
+  fr_reduce_512<EXACT>(r, prod, unc);
+}
+__device__ __forceinline__ void fr_sqr(u32 (&r)[8], const u32 (&a)[8]) {
+  u32 unused = 0;
+  fr_sqr_t<true>(r, a, unused);
 }
 
 // power5 : field_arithmetic.cpp:332-338
-__device__ __forceinline__ void fr_pow5(u32 (&r)[8], const u32 (&a)[8]) {
+template <bool EXACT>
+__device__ __forceinline__ void fr_pow5_t(u32 (&r)[8], const u32 (&a)[8], u32 &unc) {
   u32 a2[8], a4[8];
-  fr_sqr(a2, a);
-  fr_sqr(a4, a2);
-  fr_mul(r, a4, a);
+  fr_sqr_t<EXACT>(a2, a, unc);
+  fr_sqr_t<EXACT>(a4, a2, unc);
+  fr_mul_t<EXACT>(r, a4, a, unc);
+}
+__device__ __forceinline__ void fr_pow5(u32 (&r)[8], const u32 (&a)[8]) {
+  u32 unused = 0;
+  fr_pow5_t<true>(r, a, unused);
 }
 
 }  // namespace cuzk

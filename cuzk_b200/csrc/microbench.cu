@@ -79,6 +79,24 @@ __global__ void __launch_bounds__(256) imad_peak_kernel(u32 *sink, int iters, u3
       } else if (VARIANT == 8) {   // SEL
 #pragma unroll
         for (int i = 0; i < 16; ++i) asm volatile("{.reg .pred p; setp.ne.u32 p, %1, 0; selp.u32 %0, %0, %2, p;}" : "+r"(lo[i]) : "r"(b), "r"(hi[i]));
+      } else if (VARIANT == 10) {  // IMAD.WIDE.U32 with an immediate multiplier (the form of every product by k, W - p, MDS)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) mad_wide(lo[i], hi[i], lo[i], 0x9f60cd29u + 2u * i);
+      } else if (VARIANT == 11) {  // IMAD.WIDE.U32 with the multiplier in the constant bank (kernel parameter)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) mad_wide(lo[i], hi[i], lo[i], seed);
+      } else if (VARIANT == 12) {  // immediate-form carry chains: four chains of four lanes, as in mul_wide_8x8(high, k)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          lo[4 * c] = mad_lo_cc(lo[4 * c], 0x4ffffffbu, lo[4 * c]);
+          hi[4 * c] = madc_hi_cc(lo[4 * c], 0x4ffffffbu, hi[4 * c]);
+#pragma unroll
+          for (int j = 1; j < 4; ++j) {
+            const u32 m = hi[4 * c + j - 1];
+            lo[4 * c + j] = madc_lo_cc(m, 0x9f60cd29u + 2u * j, lo[4 * c + j]);
+            hi[4 * c + j] = madc_hi_cc(m, 0x9f60cd29u + 2u * j, hi[4 * c + j]);
+          }
+        }
       } else if (VARIANT == 9) {   // DFMA (FP64 pipe), 8 lanes
         double *d = reinterpret_cast<double *>(lo);  // 8 doubles over lo[16]
 #pragma unroll
@@ -123,6 +141,9 @@ extern "C" int cuzk_imad_peak(int variant, int iters, double *ops_per_second_out
       case 7: imad_peak_kernel<7><<<blocks, threads>>>(sink, iters, 1u + rep); break;
       case 8: imad_peak_kernel<8><<<blocks, threads>>>(sink, iters, 1u + rep); break;
       case 9: imad_peak_kernel<9><<<blocks, threads>>>(sink, iters, 1u + rep); break;
+      case 10: imad_peak_kernel<10><<<blocks, threads>>>(sink, iters, 1u + rep); break;
+      case 11: imad_peak_kernel<11><<<blocks, threads>>>(sink, iters, 1u + rep); break;
+      case 12: imad_peak_kernel<12><<<blocks, threads>>>(sink, iters, 1u + rep); break;
       default: cudaFree(sink); return CUZK_ERR_INVALID;
     }
     cudaEventRecord(e1);

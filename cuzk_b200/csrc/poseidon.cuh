@@ -31,6 +31,17 @@ __device__ __forceinline__ void arc_canon(u32 (&s)[8], int idx) {
   if (s[7] >= CUZK_P7) cond_sub_mp<1>(s);
 }
 
+// fast path: no branch; a sum whose top word reaches p's top word (2^-30) is left unreduced and reported in `unc`
+__device__ __forceinline__ void arc_fast(u32 (&s)[8], int idx, u32 &unc) {
+  const u32 c0 = c_rc[idx][0], c1 = c_rc[idx][1];
+  s[0] = add_cc(s[0], c0);
+  s[1] = addc_cc(s[1], c1);
+#pragma unroll
+  for (int i = 2; i < 7; ++i) s[i] = addc_cc(s[i], 0u);
+  s[7] = addc(s[7], 0u);
+  unc |= ((s[7] >> CUZK_UNC_WIDEN) >= (CUZK_P7 >> CUZK_UNC_WIDEN)) ? 1u : 0u;
+}
+
 // same for an arbitrary 256-bit s (first round of a caller-supplied state): wraps mod 2^256, full reduce
 __device__ __forceinline__ void arc_general(u32 (&s)[8], int idx) {
   const u32 c0 = c_rc[idx][0], c1 = c_rc[idx][1];
@@ -99,15 +110,7 @@ __device__ __forceinline__ void mds_row(u32 (&n)[8], const u32 (&s0)[8], const u
 }
 
 // exact MDS layer, term by term as the reference evaluates it (also the fallback of mds_fast)
-#ifndef CUZK_MDS_EXACT_INLINE
-#define CUZK_MDS_EXACT_INLINE 1
-#endif
-#if CUZK_MDS_EXACT_INLINE
-__device__ __forceinline__
-#else
-__device__ __noinline__
-#endif
-void mds_exact(u32 (&s0)[8], u32 (&s1)[8], u32 (&s2)[8]) {
+__device__ __forceinline__ void mds_exact(u32 (&s0)[8], u32 (&s1)[8], u32 (&s2)[8]) {
   u32 n0[8], n1[8], n2[8];
   mds_row<7, 23, 8>(n0, s0, s1, s2);
   mds_row<26, 5, 4>(n1, s0, s1, s2);
@@ -202,43 +205,62 @@ __device__ __forceinline__ void mds_row_fast(u32 (&n)[8], u32 &unc, const u32 (&
 #pragma unroll
   for (int i = 2; i < 7; ++i) n[i] = addc_cc(ye[i], yo[i]);
   n[7] = addc(ye[7], yo[7]);
-  cond_sub_mp<1>(n);
+  cond_sub_top<1>(n, unc);
 }
 
-__device__ __forceinline__ void mds(u32 (&s0)[8], u32 (&s1)[8], u32 (&s2)[8]) {
+// fast MDS layer: undecided wrap bits / comparisons are reported in `unc`, the state is then meaningless and the caller
+// recomputes its unit on the exact path
+__device__ __forceinline__ void mds_fast(u32 (&s0)[8], u32 (&s1)[8], u32 (&s2)[8], u32 &unc) {
   u32 n0[8], n1[8], n2[8];
-  u32 unc = 0;
   mds_row_fast<7, 23, 8>(n0, unc, s0, s1, s2);
   mds_row_fast<26, 5, 4>(n1, unc, s0, s1, s2);
   mds_row_fast<15, 20, 9>(n2, unc, s0, s1, s2);
-  if (unc != 0) {   // ~2^-24 per layer: recompute exactly, term by term
-    mds_exact(s0, s1, s2);
-    return;
-  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s0[i] = n0[i]; s1[i] = n1[i]; s2[i] = n2[i]; }
 }
 
-__device__ __forceinline__ void sbox(u32 (&s)[8]) {
+// one layer with its own fallback (test hook cuzk_debug_mds_layer only)
+__device__ __forceinline__ void mds(u32 (&s0)[8], u32 (&s1)[8], u32 (&s2)[8]) {
+  u32 t0[8], t1[8], t2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { t0[i] = s0[i]; t1[i] = s1[i]; t2[i] = s2[i]; }
+  u32 unc = 0;
+  mds_fast(t0, t1, t2, unc);
+  if (unc != 0) {
+    mds_exact(s0, s1, s2);
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s0[i] = t0[i]; s1[i] = t1[i]; s2[i] = t2[i]; }
+}
+
+template <bool EXACT>
+__device__ __forceinline__ void sbox(u32 (&s)[8], u32 &unc) {
   u32 r[8];
-  fr_pow5(r, s);
+  fr_pow5_t<EXACT>(r, s, unc);
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = r[i];
 }
 
 // permutation : poseidon.cpp:60-87.  CANON = every state word is already < p on entry.
-template <bool CANON>
-__device__ __forceinline__ void permute(u32 (&s0)[8], u32 (&s1)[8], u32 (&s2)[8]) {
+// EXACT = false is the production path: top-word reductions, linear-form MDS; any undecided comparison sets `unc` and the
+// caller recomputes the unit with EXACT = true (the reference's evaluation order, step by step).
+template <bool CANON, bool EXACT>
+__device__ __forceinline__ void permute_t(u32 (&s0)[8], u32 (&s1)[8], u32 (&s2)[8], u32 &unc) {
 #pragma unroll 1
   for (int round = 0; round < kRounds; ++round) {
     if (!CANON && round == 0) {
       arc_general(s0, 0);
       arc_general(s1, 1);
       arc_general(s2, 2);
-    } else {
+    } else if (EXACT) {
       arc_canon(s0, 3 * round);
       arc_canon(s1, 3 * round + 1);
       arc_canon(s2, 3 * round + 2);
+    } else {
+      arc_fast(s0, 3 * round, unc);
+      arc_fast(s1, 3 * round + 1, unc);
+      arc_fast(s2, 3 * round + 2, unc);
     }
     const bool full = (round < kFullHalf) || (round >= kFullHalf + kPartial);
     const int nsbox = full ? 3 : 1;
@@ -246,7 +268,7 @@ __device__ __forceinline__ void permute(u32 (&s0)[8], u32 (&s1)[8], u32 (&s2)[8]
     // the next element sits in s0 (three rotations restore the order).
 #pragma unroll 1
     for (int i = 0; i < nsbox; ++i) {
-      sbox(s0);
+      sbox<EXACT>(s0, unc);
       if (full) {
 #pragma unroll
         for (int w = 0; w < 8; ++w) {
@@ -257,8 +279,21 @@ __device__ __forceinline__ void permute(u32 (&s0)[8], u32 (&s1)[8], u32 (&s2)[8]
         }
       }
     }
-    mds(s0, s1, s2);
+    if (EXACT) mds_exact(s0, s1, s2);
+    else mds_fast(s0, s1, s2, unc);
   }
+}
+
+// exact permutation, out of line: one copy per module, reached only from the rare fallback paths
+__device__ unsigned long long g_exact_fallbacks;   // how many units took the exact path (cuzk_debug_fallback_count)
+__device__ __noinline__ void permute_exact(u32 *st, int canon) {
+  u32 s0[8], s1[8], s2[8], unused = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s0[i] = st[i]; s1[i] = st[8 + i]; s2[i] = st[16 + i]; }
+  if (canon) permute_t<true, true>(s0, s1, s2, unused);
+  else permute_t<false, true>(s0, s1, s2, unused);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { st[i] = s0[i]; st[8 + i] = s1[i]; st[16 + i] = s2[i]; }
 }
 
 // sponge absorb step: state[i] = add(state[i], x) for a possibly non-canonical x and canonical state
@@ -291,27 +326,66 @@ __device__ __forceinline__ void set_small(u32 (&x)[8], u32 v) {
   for (int i = 1; i < 8; ++i) x[i] = 0;
 }
 
-// hash_multiple / device sponge over `width` children (poseidon.cpp:98-126; domain separator DS):
-// absorbs two per permutation, a final odd child alone; width == 0 -> zero permutations -> output 0.
+// hash_multiple / device sponge over `width` inputs (poseidon.cpp:98-126; domain separator ds_hi:ds_lo):
+// absorbs two per permutation, a final odd input alone; width == 0 -> zero permutations -> output 0.
+// `load(x, i)` must be repeatable: when the fast pass reports an undecided comparison the whole sponge is evaluated
+// again on the exact path.
+template <class Loader>
+__device__ __forceinline__ void sponge_n(u32 (&out)[8], u32 ds_lo, u32 ds_hi, int width, Loader load) {
+  u32 unc = 0;
+  {
+    u32 s0[8], s1[8], s2[8];
+    set_small(s0, ds_lo);
+    s0[1] = ds_hi;
+    set_small(s1, 0);
+    set_small(s2, 0);
+#pragma unroll 1
+    for (int i = 0; i < width; i += 2) {
+      u32 x[8];
+      load(x, i);
+      absorb(s1, x);
+      if (i + 1 < width) {
+        load(x, i + 1);
+        absorb(s2, x);
+      }
+      permute_t<true, false>(s0, s1, s2, unc);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] = s1[i];
+  }
+  if (unc != 0) {   // ~1e-6 per permutation on random data
+    atomicAdd(&g_exact_fallbacks, 1ull);
+    u32 st[24];
+#pragma unroll
+    for (int i = 0; i < 24; ++i) st[i] = 0;
+    st[0] = ds_lo;
+    st[1] = ds_hi;
+#pragma unroll 1
+    for (int i = 0; i < width; i += 2) {
+      u32 x[8], a[8];
+      load(x, i);
+#pragma unroll
+      for (int w = 0; w < 8; ++w) a[w] = st[8 + w];
+      absorb(a, x);
+#pragma unroll
+      for (int w = 0; w < 8; ++w) st[8 + w] = a[w];
+      if (i + 1 < width) {
+        load(x, i + 1);
+#pragma unroll
+        for (int w = 0; w < 8; ++w) a[w] = st[16 + w];
+        absorb(a, x);
+#pragma unroll
+        for (int w = 0; w < 8; ++w) st[16 + w] = a[w];
+      }
+      permute_exact(st, 1);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] = st[8 + i];
+  }
+}
 template <class Loader>
 __device__ __forceinline__ void sponge_n(u32 (&out)[8], u32 ds, int width, Loader load) {
-  u32 s0[8], s1[8], s2[8];
-  set_small(s0, ds);
-  set_small(s1, 0);
-  set_small(s2, 0);
-#pragma unroll 1
-  for (int i = 0; i < width; i += 2) {
-    u32 x[8];
-    load(x, i);
-    absorb(s1, x);
-    if (i + 1 < width) {
-      load(x, i + 1);
-      absorb(s2, x);
-    }
-    permute<true>(s0, s1, s2);
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) out[i] = s1[i];
+  sponge_n(out, ds, 0u, width, load);
 }
 
 }  // namespace cuzk

@@ -160,10 +160,15 @@ int cuzk_synth_u64_leaves(uint64_t *out, size_t n, uint64_t seed, uint64_t start
  * canonical 3-element states; mode 0 = the production fast path with its exact fallback, 1 = exact path only */
 int cuzk_debug_mds_layer(uint64_t *states, size_t n, int mode, void *stream);
 
+/* how many units (hashes, nodes, proof levels, states) were evaluated a second time on the exact path because the fast
+ * path met a comparison its top-word test could not decide (about 1e-6 per permutation on random data); a blocking read */
+uint64_t cuzk_debug_fallback_count(void);
+
 /* integer-multiply pipe microbenchmark: runs `iters` rounds of dependent-free IMAD.WIDE chains on the whole
  * chip and returns measured 32x32->64 multiply-adds per second (the roofline denominator); variant selects
  * 0 = IMAD.WIDE.U32, 1 = IMAD (lo), 2 = IMAD.HI, 3 = IMAD.WIDE.U32.X carry chains, 4 = IADD3.X carry chains,
- * 5/6/7 = IMAD.WIDE with 1/2/3 carry-chain adds per multiply (counts the multiplies), 8 = SEL, 9 = DFMA */
+ * 5/6/7 = IMAD.WIDE with 1/2/3 carry-chain adds per multiply (counts the multiplies), 8 = SEL, 9 = DFMA,
+ * 10 = IMAD.WIDE.U32 with an immediate multiplier, 11 = multiplier in the constant bank, 12 = immediate-form carry chains */
 int cuzk_imad_peak(int variant, int iters, double *ops_per_second_out);
 
 #ifdef __cplusplus
