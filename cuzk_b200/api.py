@@ -156,7 +156,7 @@ class CudaPoseidonHash:
 
     @staticmethod
     def get_optimal_batch_size() -> int:
-        return 148 * 512  # one resident wave: 148 SMs x 4 CTAs x 128 threads
+        return 148 * 6 * 128  # one resident wave: 148 SMs x 6 CTAs x 128 threads
 
     @staticmethod
     def get_max_batch_size() -> int:

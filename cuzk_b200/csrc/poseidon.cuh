@@ -208,13 +208,81 @@ __device__ __forceinline__ void mds_row_fast(u32 (&n)[8], u32 &unc, const u32 (&
   cond_sub_top<1>(n, unc);
 }
 
+// ---- the same row on the FP64 pipe ---------------------------------------------------------------------------
+// B200 issues DFMA at full rate (62 per SM per clock measured, csrc/microbench.cu variant 9) on a pipe the rest of the
+// permutation never touches, while the 32x32->64 multiplier (IMAD.WIDE, ~28 per SM per clock) is the kernel's bound.
+// Every product of this row has a factor below 2^6, so all of them are exact in double precision:
+//   lane sums   S_m = C0*s0[m] + C1*s1[m] + C2*s2[m]          < 2^39
+//   y_m         = S_m + q * (W - p)[m]                         < 2^40        (q < 2^6)
+// Limbs enter as doubles through the 2^52 bias trick (no I2F), lanes leave the same way; the quotient estimate is
+// evaluated in double with round-toward-zero so that it never exceeds floor(X / p), X = S - wsum * k, and is at most
+// one below it (the dropped terms lower the estimate by < 1e-7 quotient units).
+#ifndef CUZK_MDS_FP64
+#define CUZK_MDS_FP64 1
+#endif
+#define CUZK_TWO52 4503599627370496.0
+#ifndef CUZK_FP64_CVT
+#define CUZK_FP64_CVT 0   // 0: 2^52 bias trick (register-pair moves + DADD); 1: I2F / F2I conversion instructions
+#endif
+__device__ __forceinline__ double u32_as_double(u32 x) {
+#if CUZK_FP64_CVT
+  return (double)x;
+#else
+  return __hiloint2double(0x43300000, (int)x) - CUZK_TWO52;
+#endif
+}
+
+template <u32 C0, u32 C1, u32 C2>
+__device__ __forceinline__ void mds_row_fp64(u32 (&n)[8], u32 &unc, const u32 (&s0)[8], const u32 (&s1)[8], const u32 (&s2)[8]) {
+  u32 wsum = 0;
+  mds_wrap_bit<C0>(wsum, unc, s0);
+  mds_wrap_bit<C1>(wsum, unc, s1);
+  mds_wrap_bit<C2>(wsum, unc, s2);
+  double S[8];
+#pragma unroll
+  for (int m = 0; m < 8; ++m)
+    S[m] = fma((double)C0, u32_as_double(s0[m]), fma((double)C1, u32_as_double(s1[m]), (double)C2 * u32_as_double(s2[m])));
+  // quotient estimate: v <= S / 2^224, L <= X / 2^228, qhat = floor(L * c) with c <= 2^228 / p  =>  q - 1 <= qhat <= q
+  const double wd = u32_as_double(wsum);
+  const double v = __fma_rz(S[6], 0x1p-32, S[7]);
+  const double L = __fma_rz(v, 0.0625, -(wd * 14722940.125));            // (K7 + 1) / 16 = 14722940.125 exactly
+  const double qhat = __fma_rz(L, 0x1.5291d188b15fap-26, CUZK_TWO52) - CUZK_TWO52;   // 16 / (p7 + 1), rounded down
+  const double q = fma(-5.0, wd, qhat);                                   // >= 0 (see mds_row_fast)
+  // y = S + q * (W - p)  (mod W): lanes back to integers, one carry chain
+  u32 lo[8], hi[8];
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+#if CUZK_FP64_CVT
+    const u64 y = __double2ull_rz(fma(q, (double)np_limb(m), S[m]));
+    lo[m] = (u32)y;
+    hi[m] = (u32)(y >> 32);
+#else
+    const double y = fma(q, (double)np_limb(m), S[m]) + CUZK_TWO52;
+    lo[m] = (u32)__double2loint(y);
+    hi[m] = (u32)__double2hiint(y) & 0x000FFFFFu;
+#endif
+  }
+  n[0] = lo[0];
+  n[1] = add_cc(lo[1], hi[0]);
+#pragma unroll
+  for (int i = 2; i < 7; ++i) n[i] = addc_cc(lo[i], hi[i - 1]);
+  n[7] = addc(lo[7], hi[6]);
+  cond_sub_top<1>(n, unc);
+}
+
 // fast MDS layer: undecided wrap bits / comparisons are reported in `unc`, the state is then meaningless and the caller
 // recomputes its unit on the exact path
 __device__ __forceinline__ void mds_fast(u32 (&s0)[8], u32 (&s1)[8], u32 (&s2)[8], u32 &unc) {
   u32 n0[8], n1[8], n2[8];
+#if CUZK_MDS_FP64
+  mds_row_fp64<7, 23, 8>(n0, unc, s0, s1, s2);
+  mds_row_fp64<26, 5, 4>(n1, unc, s0, s1, s2);
+  mds_row_fp64<15, 20, 9>(n2, unc, s0, s1, s2);
+#else
   mds_row_fast<7, 23, 8>(n0, unc, s0, s1, s2);
   mds_row_fast<26, 5, 4>(n1, unc, s0, s1, s2);
   mds_row_fast<15, 20, 9>(n2, unc, s0, s1, s2);
+#endif
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s0[i] = n0[i]; s1[i] = n1[i]; s2[i] = n2[i]; }
 }

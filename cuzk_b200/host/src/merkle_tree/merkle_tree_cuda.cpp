@@ -236,7 +236,7 @@ void CudaNaryMerkleTree::cleanup_cuda() {
 size_t CudaNaryMerkleTree::get_optimal_batch_size() {
   cuzk_device_info_t info;
   if (cuzk_device_info(0, &info) != CUZK_OK) return 1024;
-  return (size_t)info.sm_count * 7 * 128;
+  return (size_t)info.sm_count * 6 * 128;
 }
 size_t CudaNaryMerkleTree::get_max_batch_size() { return (size_t)1 << 31; }
 

@@ -25,7 +25,7 @@ CudaPoseidonHash::CudaPoseidonHash() : initialized_(false), optimal_batch_size_(
   }
   cuzk_device_info_t info;
   const int sms = (cuzk_device_info(0, &info) == CUZK_OK) ? info.sm_count : 148;
-  optimal_batch_size_ = (size_t)sms * 7 * 128;  // one resident wave: 7 CTAs of 128 one-hash threads per SM
+  optimal_batch_size_ = (size_t)sms * 6 * 128;  // one resident wave: 6 CTAs of 128 one-hash threads per SM
   max_batch_size_ = (size_t)1 << 31;            // the library chunks host batches itself; this is a sanity bound
   initialized_ = true;
 }

@@ -45,19 +45,37 @@ def library_is_stale() -> bool:
     return any(os.path.getmtime(s) > t for s in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile libcuzk_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
-    if not force and not library_is_stale():
-        return LIB_PATH
+def _compile(out_path: str, extra: list[str], verbose: bool = False) -> None:
     nvcc = os.environ.get("NVCC", "nvcc")
     cu = [s for s in _sources() if s.endswith(".cu")]
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + cu
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out_path] + cu
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise CuzkError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile libcuzk_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    if not force and not library_is_stale():
+        return LIB_PATH
+    _compile(LIB_PATH, [], verbose)
     return LIB_PATH
+
+
+# Test-only build of the same sources in which the fast path's "undecided comparison" flags also fire on near misses
+# (top 12 bits equal instead of all 32), so that a large share of the units takes the exact fallback path.  The
+# results must not change; tests/test_gpu_parity.py runs the parity checks against this library too.
+DEBUG_LIB_PATH = os.path.join(PKG_DIR, "libcuzk_b200_widen.so")
+
+
+def build_debug_library(force: bool = False) -> str:
+    deps = _sources() + [os.path.join(ROOT, "include", "cuzk_b200.h")]
+    fresh = os.path.exists(DEBUG_LIB_PATH) and all(os.path.getmtime(s) <= os.path.getmtime(DEBUG_LIB_PATH) for s in deps)
+    if force or not fresh:
+        _compile(DEBUG_LIB_PATH, ["-DCUZK_UNC_WIDEN=20"])
+    return DEBUG_LIB_PATH
 
 
 _SIGS = {

@@ -186,7 +186,7 @@ TEST_F(HostPoseidon, LargeBatchCrossesPipelineChunks) {
     cuzk_oracle_hash_pair(l[i].limbs, r[i].limbs, want.limbs);
     bad += got[i] != want;
   }
-  for (size_t i : {size_t(0), size_t(132607), size_t(132608), size_t(265215), size_t(265216), n - 1}) {
+  for (size_t i : {size_t(0), size_t(113663), size_t(113664), size_t(227327), size_t(227328), n - 1}) {
     FieldElement want;
     cuzk_oracle_hash_pair(l[i].limbs, r[i].limbs, want.limbs);
     bad += got[i] != want;

@@ -410,3 +410,56 @@ def test_config4_octary_2p26_sharded_equals_full_build(gpu, oracle):
         out = torch.empty((1, 4), dtype=torch.int64, device="cuda")
         L.check(L.cuzk_merkle_top_root(nodes.data_ptr(), plan.total_subtrees, arity, out.data_ptr(), 0, None), "top_root")
         assert (to_host(out)[0] == root).all(), world
+
+
+def test_exact_fallback_path_is_bit_exact(gpu, oracle):
+    """The production kernels evaluate every unit on a fast path whose top-word comparisons can be undecided (2^-32 each);
+    such units are recomputed on the exact path.  libcuzk_b200_widen.so is the same source built with the flags widened
+    to near misses, so a large share of the units takes the fallback: every result must still equal the oracle."""
+    import os
+
+    import torch
+
+    from cuzk_b200 import lib
+
+    path = lib.DEBUG_LIB_PATH
+    assert os.path.exists(path), "libcuzk_b200_widen.so missing: run __graft_entry__.build()"
+    D = lib.Lib(path)
+    D.check(D.cuzk_init(0), "init(widen)")
+    try:
+        before = D.cuzk_debug_fallback_count()
+        n = 20_000
+        l, r = synth_elements(21, n), synth_elements(22, n)
+        dl, dr = to_dev(l), to_dev(r)
+        out = torch.empty_like(dl)
+        D.check(D.cuzk_poseidon_hash_pairs(dl.data_ptr(), dr.data_ptr(), out.data_ptr(), n, 0, None), "pairs")
+        assert (to_host(out) == oracle.hash_pairs(l, r)).all()
+        D.check(D.cuzk_poseidon_hash_single(dl.data_ptr(), out.data_ptr(), n, 0, None), "single")
+        assert (to_host(out) == oracle.hash_single(l)).all()
+        rng = np.random.default_rng(5)
+        st = rnd(rng, 3 * 3000, False)
+        ds = to_dev(st)
+        D.check(D.cuzk_poseidon_permutation(ds.data_ptr(), 3000, 0, None), "permutation")
+        assert (to_host(ds).reshape(-1, 3, 4) == oracle.permutation(st.reshape(-1, 3, 4))).all()
+        for arity, m in ((2, 3000), (8, 5000)):
+            leaves = synth_u64_leaves(23, m) if arity == 8 else rnd(rng, m, True)
+            want = oracle.merkle_build(leaves, arity)
+            tot = sum(x.shape[0] for x in want)
+            lv = torch.empty((tot, 4), dtype=torch.int64, device="cuda")
+            D.check(D.cuzk_merkle_build(to_dev(leaves).data_ptr(), m, arity, lv.data_ptr(), 0, None), "build")
+            assert (to_host(lv) == np.concatenate(want)).all()
+            L = len(want) - 1
+            idx = torch.arange(0, m, 7, dtype=torch.int64, device="cuda")
+            q = idx.numel()
+            sib = torch.empty((q, L, arity - 1, 4), dtype=torch.int64, device="cuda")
+            pos = torch.empty((q, L), dtype=torch.int32, device="cuda")
+            D.check(D.cuzk_merkle_prove_batch(lv.data_ptr(), m, arity, idx.data_ptr(), q, sib.data_ptr(), pos.data_ptr(), 0, None), "prove")
+            res = torch.empty(q, dtype=torch.uint8, device="cuda")
+            vals = to_dev(leaves)[idx].contiguous()
+            D.check(D.cuzk_merkle_verify_batch(vals.data_ptr(), sib.data_ptr(), pos.data_ptr(), L, arity, lv[-1:].data_ptr(), res.data_ptr(), q, 0, None), "verify")
+            assert bool(res.all())
+        torch.cuda.synchronize()
+        taken = D.cuzk_debug_fallback_count() - before
+        assert taken > 1000, f"the widened build should take the exact path often, took it {taken} times"
+    finally:
+        D.cuzk_shutdown()
