@@ -392,3 +392,96 @@ class CudaNaryMerkleTree:
             return False
         res = self.verify_batch_proofs(proofs, leaf_values, root)
         return bool(res.all())
+
+
+class DeviceMerkleTree:
+    """Device-resident tree handle (cuzk_tree_*): the level arrays stay in HBM, proofs are generated and verified against
+    them there, and leaves can be updated incrementally (path re-hash instead of the reference's full rebuild,
+    merkle_tree.cpp:290-301).  Inputs/outputs are numpy arrays (host) or int64 CUDA tensors (device), as elsewhere."""
+
+    def __init__(self, leaves, arity: int = 2):
+        import ctypes as C
+
+        if not (2 <= arity <= 8):
+            raise ValueError(f"arity must be between 2 and 8, got {arity}")
+        initialize()
+        x = _elems(leaves)
+        if x.shape[0] == 0:
+            raise CuzkError("DeviceMerkleTree needs at least one leaf")
+        lib = get_lib()
+        h = C.c_void_p()
+        lib.check(lib.cuzk_tree_build(_ptr(x), x.shape[0], arity, _mem(x), _stream(x), C.byref(h)), "cuzk_tree_build")
+        self._h, self.arity, self.leaf_count = h, arity, x.shape[0]
+        self.num_levels = lib.cuzk_tree_num_levels(h)
+        self.total_nodes = lib.cuzk_tree_total_nodes(h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            get_lib().cuzk_tree_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def get_root_hash(self) -> np.ndarray:
+        out = np.empty(4, dtype=np.uint64)
+        lib = get_lib()
+        lib.check(lib.cuzk_tree_root(self._h, out.ctypes.data, MEM_HOST, None), "cuzk_tree_root")
+        return out
+
+    def get_tree_levels(self):
+        """every level as host arrays (one download), level 0 = padded leaves, last = root"""
+        flat = np.empty((self.total_nodes, 4), dtype=np.uint64)
+        lib = get_lib()
+        lib.check(lib.cuzk_tree_levels(self._h, flat.ctypes.data, MEM_HOST, None), "cuzk_tree_levels")
+        out, off, p = [], 0, padded_leaves(self.leaf_count, self.arity)
+        while True:
+            out.append(flat[off : off + p])
+            off += p
+            if p == 1:
+                return out
+            p //= self.arity
+
+    def generate_batch_proofs(self, indices) -> MerkleProofBatch:
+        lib = get_lib()
+        L = self.num_levels - 1
+        dev = _is_tensor(indices)
+        if dev:
+            idx = indices.to(torch.int64).contiguous()
+            q = idx.numel()
+            sib = torch.empty((q, L, self.arity - 1, 4), dtype=torch.int64, device=idx.device)
+            pos = torch.empty((q, L), dtype=torch.int32, device=idx.device)
+        else:
+            idx = np.ascontiguousarray(indices, dtype=np.uint64)
+            q = idx.size
+            sib = np.empty((q, L, self.arity - 1, 4), dtype=np.uint64)
+            pos = np.empty((q, L), dtype=np.uint32)
+        if q and L:
+            lib.check(lib.cuzk_tree_prove_batch(self._h, _ptr(idx), q, _ptr(sib), _ptr(pos), MEM_DEVICE if dev else MEM_HOST,
+                                                _stream(idx)), "cuzk_tree_prove_batch")
+        return MerkleProofBatch(sib, pos, idx, self.arity)
+
+    def verify_batch_proofs(self, proofs: MerkleProofBatch, leaf_values):
+        lib = get_lib()
+        lv = _elems(leaf_values)
+        q = lv.shape[0]
+        if q != len(proofs):
+            raise CuzkError("size mismatch")
+        dev = _is_tensor(lv)
+        res = torch.empty(q, dtype=torch.uint8, device=lv.device) if dev else np.empty(q, dtype=np.uint8)
+        if q:
+            lib.check(lib.cuzk_tree_verify_batch(self._h, _ptr(lv), _ptr(proofs.siblings), _ptr(proofs.positions), _ptr(res), q,
+                                                 MEM_DEVICE if dev else MEM_HOST, _stream(lv)), "cuzk_tree_verify_batch")
+        return res
+
+    def update_leaves(self, indices, values) -> None:
+        """values[q] replaces leaf indices[q] (distinct indices < leaf_count); only the ancestors are re-hashed"""
+        lib = get_lib()
+        v = _elems(values)
+        dev = _is_tensor(v)
+        idx = indices.to(torch.int64).contiguous() if dev else np.ascontiguousarray(indices, dtype=np.uint64)
+        lib.check(lib.cuzk_tree_update_leaves(self._h, _ptr(idx), _ptr(v), v.shape[0], MEM_DEVICE if dev else MEM_HOST, _stream(v)),
+                  "cuzk_tree_update_leaves")

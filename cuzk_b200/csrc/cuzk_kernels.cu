@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -305,6 +306,29 @@ __global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) merkle_fused2_kernel(
     x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
   });
   store_fr(out + 2 * i, r);
+}
+
+// incremental update, step 0: write the new leaf values (level 0)
+__global__ void merkle_write_leaves_kernel(uint4 *__restrict__ level0, const u64 *__restrict__ indices, const uint4 *__restrict__ values,
+                                           size_t count) {
+  size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= count) return;
+  const u64 idx = indices[q];
+  level0[2 * idx] = values[2 * q];
+  level0[2 * idx + 1] = values[2 * q + 1];
+}
+// incremental update, one level: thread q re-hashes the level-`shift_level` ancestor of leaf indices[q] from its children.
+// Updates that share an ancestor compute the same value and store it twice (benign).  in = level l-1, out = level l.
+__global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) merkle_update_level_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out,
+                                                                      const u64 *__restrict__ indices, size_t count, u64 divisor,
+                                                                      int arity) {
+  size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= count) return;
+  const size_t node = indices[q] / divisor;          // ancestor index at the output level (divisor = arity^l)
+  const uint4 *kids = in + 2 * node * (size_t)arity;
+  u32 r[8];
+  sponge_n(r, 3u, arity, [&](u32(&x)[8], int j) { load_fr_plain(x, kids + 2 * j); });
+  store_fr(out + 2 * node, r);
 }
 
 // proofs from level arrays: one thread per (proof, level)
@@ -1047,6 +1071,163 @@ int cuzk_merkle_verify_batch(const uint64_t *leaf_values, const uint64_t *siblin
                              (int)levels, (int)arity, static_cast<const uint4 *>(droot), static_cast<uint8_t *>(d_out), m);
                          return check_launch("merkle_verify_kernel");
                        });
+}
+
+// ---- device-resident tree handle ----
+struct cuzk_tree {
+  uint64_t *levels = nullptr;   // device, level-major, cuzk_merkle_total_nodes elements
+  size_t n = 0, padded = 0, total = 0, nlevels = 0;
+  unsigned arity = 0;
+  int device = 0;
+};
+
+int cuzk_tree_build(const uint64_t *leaves, size_t n, unsigned arity, int mem, void *stream, cuzk_tree_t **out) {
+  int rc = require_init();
+  if (rc) return rc;
+  if ((rc = check_arity(arity))) return rc;
+  if (!out) return fail(CUZK_ERR_INVALID, "null pointer");
+  *out = nullptr;
+  if (n == 0 || !leaves) return fail(CUZK_ERR_INVALID, "cuzk_tree_build: needs at least one leaf");
+  cuzk_tree *t = new (std::nothrow) cuzk_tree;
+  if (!t) return fail(CUZK_ERR_INVALID, "out of host memory");
+  t->n = n;
+  t->arity = arity;
+  t->padded = cuzk_merkle_padded_leaves(n, arity);
+  t->total = cuzk_merkle_total_nodes(n, arity);
+  t->nlevels = cuzk_merkle_num_levels(n, arity);
+  t->device = g_device;
+  cudaStream_t st = S(stream);
+  cudaError_t e = cudaMalloc(&t->levels, t->total * 32);
+  if (e != cudaSuccess) { delete t; return cuda_fail(e, "cudaMalloc(tree levels)"); }
+  if (mem == CUZK_MEM_DEVICE) {
+    rc = merkle_build_dev(leaves, n, arity, t->levels, st);
+  } else {
+    std::lock_guard<std::mutex> lk(g_hp_mu);
+    void *dl;
+    if (!(rc = ws_get(0, n * 32, &dl))) {
+      e = cudaMemcpyAsync(dl, leaves, n * 32, cudaMemcpyHostToDevice, st);
+      rc = e == cudaSuccess ? merkle_build_dev(static_cast<uint64_t *>(dl), n, arity, t->levels, st) : cuda_fail(e, "cudaMemcpyAsync");
+      if (!rc && (e = cudaStreamSynchronize(st)) != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize");
+    }
+  }
+  if (rc) {
+    cudaFree(t->levels);
+    delete t;
+    return rc;
+  }
+  *out = t;
+  return CUZK_OK;
+}
+
+int cuzk_tree_free(cuzk_tree_t *t) {
+  if (!t) return CUZK_OK;
+  cudaError_t e = cudaFree(t->levels);
+  delete t;
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFree(tree levels)");
+  return CUZK_OK;
+}
+
+size_t cuzk_tree_leaf_count(const cuzk_tree_t *t) { return t ? t->n : 0; }
+size_t cuzk_tree_num_levels(const cuzk_tree_t *t) { return t ? t->nlevels : 0; }
+size_t cuzk_tree_total_nodes(const cuzk_tree_t *t) { return t ? t->total : 0; }
+unsigned cuzk_tree_arity(const cuzk_tree_t *t) { return t ? t->arity : 0; }
+const uint64_t *cuzk_tree_device_levels(const cuzk_tree_t *t) { return t ? t->levels : nullptr; }
+
+int cuzk_tree_root(const cuzk_tree_t *t, uint64_t *root_out, int mem, void *stream) {
+  if (!t || !root_out) return fail(CUZK_ERR_INVALID, "null pointer");
+  cudaStream_t st = S(stream);
+  const uint64_t *src = t->levels + (t->total - 1) * 4;
+  if (mem == CUZK_MEM_DEVICE) {
+    CK(cudaMemcpyAsync(root_out, src, 32, cudaMemcpyDeviceToDevice, st));
+    return CUZK_OK;
+  }
+  CK(cudaMemcpyAsync(root_out, src, 32, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return CUZK_OK;
+}
+
+int cuzk_tree_levels(const cuzk_tree_t *t, uint64_t *levels_out, int mem, void *stream) {
+  if (!t || !levels_out) return fail(CUZK_ERR_INVALID, "null pointer");
+  cudaStream_t st = S(stream);
+  CK(cudaMemcpyAsync(levels_out, t->levels, t->total * 32, mem == CUZK_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+  if (mem != CUZK_MEM_DEVICE) CK(cudaStreamSynchronize(st));
+  return CUZK_OK;
+}
+
+int cuzk_tree_prove_batch(const cuzk_tree_t *t, const uint64_t *indices, size_t num_proofs, uint64_t *siblings_out,
+                          uint32_t *positions_out, int mem, void *stream) {
+  int rc = require_init();
+  if (rc) return rc;
+  if (!t) return fail(CUZK_ERR_INVALID, "null tree");
+  if (num_proofs == 0 || t->nlevels <= 1) return CUZK_OK;
+  if (!indices || !siblings_out || !positions_out) return fail(CUZK_ERR_INVALID, "null pointer");
+  const size_t nlv = t->nlevels - 1, threads = num_proofs * nlv, sib_bytes = threads * (t->arity - 1) * 32;
+  cudaStream_t st = S(stream);
+  auto launch = [&](const u64 *di, uint4 *ds, u32 *dp) {
+    merkle_prove_kernel<<<grid_for(threads, 256), 256, 0, st>>>(reinterpret_cast<const uint4 *>(t->levels), t->n, t->padded, (int)t->arity,
+                                                                (int)nlv, di, num_proofs, ds, dp);
+    return check_launch("merkle_prove_kernel");
+  };
+  if (mem == CUZK_MEM_DEVICE) return launch(indices, reinterpret_cast<uint4 *>(siblings_out), positions_out);
+  std::lock_guard<std::mutex> lk(g_hp_mu);
+  void *di, *ds, *dp;
+  if ((rc = ws_get(1, num_proofs * 8, &di)) || (rc = ws_get(2, sib_bytes, &ds)) || (rc = ws_get(3, threads * 4, &dp))) return rc;
+  CK(cudaMemcpyAsync(di, indices, num_proofs * 8, cudaMemcpyHostToDevice, st));
+  if ((rc = launch(static_cast<u64 *>(di), static_cast<uint4 *>(ds), static_cast<u32 *>(dp)))) return rc;
+  CK(cudaMemcpyAsync(siblings_out, ds, sib_bytes, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(positions_out, dp, threads * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return CUZK_OK;
+}
+
+int cuzk_tree_verify_batch(const cuzk_tree_t *t, const uint64_t *leaf_values, const uint64_t *siblings, const uint32_t *positions,
+                           uint8_t *results_out, size_t num_proofs, int mem, void *stream) {
+  if (!t) return fail(CUZK_ERR_INVALID, "null tree");
+  const size_t nlv = t->nlevels - 1;
+  if (mem == CUZK_MEM_DEVICE)
+    return cuzk_merkle_verify_batch(leaf_values, siblings, positions, nlv, t->arity, t->levels + (t->total - 1) * 4, results_out, num_proofs,
+                                    mem, stream);
+  uint64_t root[4];
+  int rc = cuzk_tree_root(t, root, CUZK_MEM_HOST, stream);
+  if (rc) return rc;
+  return cuzk_merkle_verify_batch(leaf_values, siblings, positions, nlv, t->arity, root, results_out, num_proofs, mem, stream);
+}
+
+int cuzk_tree_update_leaves(cuzk_tree_t *t, const uint64_t *indices, const uint64_t *values, size_t count, int mem, void *stream) {
+  int rc = require_init();
+  if (rc) return rc;
+  if (!t) return fail(CUZK_ERR_INVALID, "null tree");
+  if (count == 0) return CUZK_OK;
+  if (!indices || !values) return fail(CUZK_ERR_INVALID, "null pointer");
+  cudaStream_t st = S(stream);
+  const u64 *di = indices;
+  const uint4 *dv = reinterpret_cast<const uint4 *>(values);
+  std::unique_lock<std::mutex> lk(g_hp_mu, std::defer_lock);
+  if (mem != CUZK_MEM_DEVICE) {
+    for (size_t q = 0; q < count; ++q)   // NaryMerkleTree::update_leaf throws std::out_of_range here (merkle_tree.cpp:296-298)
+      if (indices[q] >= t->n) return fail(CUZK_ERR_INVALID, "cuzk_tree_update_leaves: leaf index out of range");
+    lk.lock();
+    void *wi, *wv;
+    if ((rc = ws_get(1, count * 8, &wi)) || (rc = ws_get(2, count * 32, &wv))) return rc;
+    CK(cudaMemcpyAsync(wi, indices, count * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(wv, values, count * 32, cudaMemcpyHostToDevice, st));
+    di = static_cast<const u64 *>(wi);
+    dv = static_cast<const uint4 *>(wv);
+  }
+  uint4 *cur = reinterpret_cast<uint4 *>(t->levels);
+  merkle_write_leaves_kernel<<<grid_for(count, 256), 256, 0, st>>>(cur, di, dv, count);
+  if ((rc = check_launch("merkle_write_leaves_kernel"))) return rc;
+  size_t p = t->padded;
+  u64 divisor = 1;
+  while (p > 1) {
+    divisor *= t->arity;
+    merkle_update_level_kernel<<<grid_for(count, kBlock), kBlock, 0, st>>>(cur, cur + 2 * p, di, count, divisor, (int)t->arity);
+    if ((rc = check_launch("merkle_update_level_kernel"))) return rc;
+    cur += 2 * p;
+    p /= t->arity;
+  }
+  if (mem != CUZK_MEM_DEVICE) CK(cudaStreamSynchronize(st));
+  return CUZK_OK;
 }
 
 int cuzk_synth_elements(uint64_t *out, size_t n, uint64_t seed, uint64_t start, int canonical, void *stream) {

@@ -105,6 +105,18 @@ _SIGS = {
     "cuzk_merkle_padding_root": (C.c_int, [C.c_uint, C.c_uint, C.c_void_p]),
     "cuzk_merkle_prove_batch": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "cuzk_merkle_verify_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "cuzk_tree_build": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "cuzk_tree_free": (C.c_int, [C.c_void_p]),
+    "cuzk_tree_leaf_count": (C.c_size_t, [C.c_void_p]),
+    "cuzk_tree_num_levels": (C.c_size_t, [C.c_void_p]),
+    "cuzk_tree_total_nodes": (C.c_size_t, [C.c_void_p]),
+    "cuzk_tree_arity": (C.c_uint, [C.c_void_p]),
+    "cuzk_tree_device_levels": (C.c_void_p, [C.c_void_p]),
+    "cuzk_tree_root": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "cuzk_tree_levels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "cuzk_tree_prove_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "cuzk_tree_verify_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "cuzk_tree_update_leaves": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "cuzk_synth_elements": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]),
     "cuzk_synth_u64_leaves": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_void_p]),
     "cuzk_debug_fallback_count": (C.c_uint64, []),

@@ -150,6 +150,34 @@ int cuzk_merkle_verify_batch(const uint64_t *leaf_values, const uint64_t *siblin
                              size_t levels, unsigned arity, const uint64_t *root, uint8_t *results_out,
                              size_t num_proofs, int mem, void *stream);
 
+/* ---- device-resident tree handle (no reference counterpart: the reference keeps every level in host vectors,
+ * merkle_tree_cuda.cuh:43, and re-uploads them per call).  The level arrays stay in HBM; proofs are generated and verified
+ * against them without the tree ever crossing PCIe again.  Same layouts as the flat calls above. ---- */
+typedef struct cuzk_tree cuzk_tree_t;
+/* CudaNaryMerkleTree::build_tree; n >= 1; `mem` describes `leaves` */
+int cuzk_tree_build(const uint64_t *leaves, size_t n, unsigned arity, int mem, void *stream, cuzk_tree_t **tree_out);
+int cuzk_tree_free(cuzk_tree_t *tree);
+size_t cuzk_tree_leaf_count(const cuzk_tree_t *tree);
+size_t cuzk_tree_num_levels(const cuzk_tree_t *tree);
+size_t cuzk_tree_total_nodes(const cuzk_tree_t *tree);
+unsigned cuzk_tree_arity(const cuzk_tree_t *tree);
+/* device pointer to the level-major node array (valid until cuzk_tree_free) */
+const uint64_t *cuzk_tree_device_levels(const cuzk_tree_t *tree);
+/* get_root_hash (merkle_tree_cuda.cuh:84): copies the 32-byte root to host or device memory */
+int cuzk_tree_root(const cuzk_tree_t *tree, uint64_t *root_out, int mem, void *stream);
+/* get_tree_levels (merkle_tree_cuda.cuh:89): copies every level out, level-major */
+int cuzk_tree_levels(const cuzk_tree_t *tree, uint64_t *levels_out, int mem, void *stream);
+/* generate_batch_proofs / verify_batch_proofs against the tree's own levels and root; layouts of cuzk_merkle_prove_batch */
+int cuzk_tree_prove_batch(const cuzk_tree_t *tree, const uint64_t *indices, size_t num_proofs, uint64_t *siblings_out,
+                          uint32_t *positions_out, int mem, void *stream);
+int cuzk_tree_verify_batch(const cuzk_tree_t *tree, const uint64_t *leaf_values, const uint64_t *siblings,
+                           const uint32_t *positions, uint8_t *results_out, size_t num_proofs, int mem, void *stream);
+/* NaryMerkleTree::update_leaf (merkle_tree.cpp:294-301; the reference rebuilds the whole tree per update) for a batch:
+ * writes values[q] at leaf indices[q] (< leaf_count, distinct) and re-hashes only the ancestors, one launch per level:
+ * count x (levels-1) x ceil(arity/2) permutations instead of a full rebuild. */
+int cuzk_tree_update_leaves(cuzk_tree_t *tree, const uint64_t *indices, const uint64_t *values, size_t count, int mem,
+                            void *stream);
+
 /* ---- synthetic inputs: generated on the device so multi-GiB leaf sets need no upload.
  * element i, limb j = splitmix64(seed, 4*(start+i)+j), top limb masked to 60 bits when canonical != 0;
  * u64 leaves: limb 0 = splitmix64(seed, start+i), other limbs 0.  Device pointers only. ---- */

@@ -463,3 +463,44 @@ def test_exact_fallback_path_is_bit_exact(gpu, oracle):
         assert taken > 1000, f"the widened build should take the exact path often, took it {taken} times"
     finally:
         D.cuzk_shutdown()
+
+
+@pytest.mark.parametrize("arity", [2, 4, 8])
+def test_device_tree_handle_and_incremental_update(gpu, oracle, arity):
+    """cuzk_tree_*: device-resident levels, proofs and verification against them, batched leaf updates by path re-hash
+    == a fresh oracle build over the updated leaves (the reference's update_leaf rebuilds the whole tree)."""
+    rng = np.random.default_rng(100 + arity)
+    n = 1000
+    leaves = rnd(rng, n, True)
+    for dev in (False, True):
+        t = gpu.DeviceMerkleTree(to_dev(leaves) if dev else leaves, arity=arity)
+        want = oracle.merkle_build(leaves, arity)
+        assert (t.get_root_hash() == want[-1][0]).all()
+        got = t.get_tree_levels()
+        assert len(got) == len(want) and all((g == w).all() for g, w in zip(got, want))
+        idx = np.unique(rng.integers(0, n, size=64)).astype(np.uint64)
+        pb = t.generate_batch_proofs(to_dev(idx.astype(np.int64)) if dev else idx)
+        sib = to_host(pb.siblings) if dev else pb.siblings
+        for k, i in enumerate(idx):
+            so, _ = oracle.merkle_prove(want, n, arity, int(i))
+            assert (sib[k] == so).all()
+        res = t.verify_batch_proofs(pb, to_dev(leaves[idx.astype(np.int64)]) if dev else leaves[idx.astype(np.int64)])
+        assert bool((res.cpu().numpy() if dev else res).all())
+        # batched update: 37 distinct leaves (first, last, a straddling group) get new values
+        upd = np.unique(np.r_[0, n - 1, n - 2, rng.integers(0, n, size=34)]).astype(np.uint64)
+        newv = rnd(rng, upd.size, False)          # non-canonical replacement values are absorbed like any leaf
+        t.update_leaves(to_dev(upd.astype(np.int64)) if dev else upd, to_dev(newv) if dev else newv)
+        leaves2 = leaves.copy()
+        leaves2[upd.astype(np.int64)] = newv
+        want2 = oracle.merkle_build(leaves2, arity)
+        got2 = t.get_tree_levels()
+        assert all((g == w).all() for g, w in zip(got2, want2)), (arity, dev)
+        # the old proofs of untouched leaves whose path was not affected may now fail; fresh proofs must verify
+        pb2 = t.generate_batch_proofs(to_dev(idx.astype(np.int64)) if dev else idx)
+        lv2 = leaves2[idx.astype(np.int64)]
+        res2 = t.verify_batch_proofs(pb2, to_dev(lv2) if dev else lv2)
+        assert bool((res2.cpu().numpy() if dev else res2).all())
+        if not dev:
+            with pytest.raises(Exception):
+                t.update_leaves(np.array([n], dtype=np.uint64), newv[:1])
+        t.close()
