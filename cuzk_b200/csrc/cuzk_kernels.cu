@@ -5,6 +5,7 @@
 // by the integer pipes (IMAD.WIDE + carry-chain IADD3), not by HBM; see DESIGN.md for the roofline.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -576,9 +577,15 @@ int fr_batch_dev(int op, const uint64_t *a, const uint64_t *b, uint64_t *out, si
   return check_launch("fr_batch_kernel");
 }
 
-// Two levels are fused per launch while the upper of the two still fills the chip; narrower levels run one launch
-// per level so that each node keeps its own thread (a fused thread hashes arity + 1 nodes back to back).
-constexpr size_t kFuseMinOut = 148 * CUZK_MIN_BLOCKS * CUZK_BLOCK;
+// Fuse two levels into one launch (merkle_fused2_kernel), or run them as two launches?  Both do the same hashing and a
+// node hash is ~190 k instructions against 288 bytes, so the saved middle-level traffic is worth nothing; what differs is
+// the tail.  A fused thread hashes arity + 1 nodes back to back, so the last, partly filled wave of CTAs costs
+// (arity + 1) node times, while per-level launches quantise in single node times.  Measured on B200 (tools/fuse_probe.py,
+// profiles/r01_fuse_probe.json): per-level launches win at every shard size (2^23 leaves, arity 8: 31.8 ms against
+// 45.2 ms fused; 2^26: 214 ms against 237 ms), so they are the default; the fused kernel stays selectable and
+// parity-tested (cuzk_debug_set_fuse).
+int g_fuse_mode = 0;   // 0: one launch per level, 1: fuse pairs of levels (cuzk_debug_set_fuse)
+inline bool fuse_two_levels(size_t /*mid_nodes*/, size_t out_nodes, unsigned /*arity*/) { return g_fuse_mode != 0 && out_nodes != 0; }
 
 int launch_level(const uint4 *in, uint4 *out, size_t in_real, size_t out_count, unsigned arity, const uint4 *pad_in, cudaStream_t st,
                  size_t ntrees = 1, size_t tree_stride = 0) {
@@ -611,7 +618,7 @@ int merkle_build_dev(const uint64_t *leaves, size_t n, unsigned arity, uint64_t 
   int level = 0;
   while (p > 1) {
     const size_t q = p / arity;
-    if (q > 1 && (q / arity) * ntrees >= kFuseMinOut) {
+    if (q > 1 && fuse_two_levels(q * ntrees, (q / arity) * ntrees, arity)) {
       const size_t q2 = q / arity;
       if ((rc = launch_fused2(cur, cur + 2 * p, cur + 2 * p + 2 * q, real, q2, arity, pad + 2 * level, st, ntrees, stride))) return rc;
       cur += 2 * p + 2 * q;
@@ -652,7 +659,8 @@ int subtree_roots_dev(const uint64_t *leaves, size_t n, unsigned arity, unsigned
   unsigned level = 0;
   int flip = 0;
   while (level < height) {
-    const unsigned step = (height - level >= 2 && ceil_div(real, (size_t)arity * arity) >= kFuseMinOut) ? 2 : 1;
+    const unsigned step =
+        (height - level >= 2 && fuse_two_levels(ceil_div(real, arity), ceil_div(real, (size_t)arity * arity), arity)) ? 2 : 1;
     const bool last = level + step == height;
     size_t out_real = ceil_div(real, arity);
     if (step == 2) out_real = ceil_div(out_real, arity);
@@ -690,6 +698,11 @@ extern "C" {
 const char *cuzk_last_error(void) { return g_err.c_str(); }
 const char *cuzk_version(void) { return "cuzk_b200 0.2 (sm_100a)"; }
 uint64_t cuzk_launch_count(void) { return g_launches.load(); }
+int cuzk_debug_set_fuse(int mode) {
+  const int old = g_fuse_mode;
+  g_fuse_mode = mode > 0 ? 1 : 0;
+  return old;
+}
 uint64_t cuzk_debug_fallback_count(void) {
   unsigned long long v = 0;
   if (cudaMemcpyFromSymbol(&v, g_exact_fallbacks, sizeof v) != cudaSuccess) return ~0ull;

@@ -188,6 +188,11 @@ int cuzk_synth_u64_leaves(uint64_t *out, size_t n, uint64_t seed, uint64_t start
  * canonical 3-element states; mode 0 = the production fast path with its exact fallback, 1 = exact path only */
 int cuzk_debug_mds_layer(uint64_t *states, size_t n, int mode, void *stream);
 
+/* Merkle builds run one launch per level by default (measured faster on B200, see csrc/cuzk_kernels.cu); mode 1 makes them
+ * fuse pairs of levels into one launch (merkle_fused2_kernel, middle level through shared memory), mode 0 restores the
+ * default.  Returns the previous mode.  Results are identical in both modes. */
+int cuzk_debug_set_fuse(int mode);
+
 /* how many units (hashes, nodes, proof levels, states) were evaluated a second time on the exact path because the fast
  * path met a comparison its top-word test could not decide (about 1e-6 per permutation on random data); a blocking read */
 uint64_t cuzk_debug_fallback_count(void);

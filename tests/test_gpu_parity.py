@@ -504,3 +504,30 @@ def test_device_tree_handle_and_incremental_update(gpu, oracle, arity):
             with pytest.raises(Exception):
                 t.update_leaves(np.array([n], dtype=np.uint64), newv[:1])
         t.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_fused_and_per_level_builds_agree_with_oracle(gpu, oracle, mode):
+    """merkle_fused2_kernel (two levels per launch, middle level through shared memory) and merkle_level_kernel give the
+    oracle's levels and subtree roots for every arity, including ragged and single-group trees."""
+    import torch
+
+    from cuzk_b200 import lib
+
+    L = lib.get_lib()
+    old = L.cuzk_debug_set_fuse(mode)
+    try:
+        rng = np.random.default_rng(mode)
+        for arity in range(2, 9):
+            for n in (arity, arity * arity, arity**3 - 1, arity**3 + 1, 700):
+                leaves = rnd(rng, n, n % 2 == 0)
+                want = oracle.merkle_build(leaves, arity)
+                t = gpu.CudaNaryMerkleTree(to_dev(leaves), arity=arity)
+                got = [to_host(x) for x in t.get_tree_levels()]
+                assert len(got) == len(want) and all((g == w).all() for g, w in zip(got, want)), (mode, arity, n)
+                # roots only (no middle level stored), whole tree as one subtree
+                root = torch.empty((1, 4), dtype=torch.int64, device="cuda")
+                L.check(L.cuzk_merkle_subtree_roots(to_dev(leaves).data_ptr(), n, arity, len(want) - 1, 1, root.data_ptr(), 0, None), "roots")
+                assert (to_host(root)[0] == want[-1][0]).all(), (mode, arity, n)
+    finally:
+        L.cuzk_debug_set_fuse(old)
