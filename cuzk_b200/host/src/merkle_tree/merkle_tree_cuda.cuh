@@ -27,65 +27,68 @@ namespace MerkleTreeCUDA {
 
 using CudaFieldElement = Poseidon::CudaFieldElement;
 
-struct CudaMerkleTreeStats;
-
 class CudaNaryMerkleTree {
-private:
-  MerkleTreeConfig config_;
-  std::vector<FieldElement> leaves_;
-  std::vector<std::vector<FieldElement>> tree_levels_;
-  size_t leaf_count_;
-  size_t tree_height_;
-
-  FieldElement compute_empty_hash(size_t arity) const;
-  void adopt_levels(const std::vector<FieldElement> &leaves, const FieldElement *flat_levels);
-
 public:
-  explicit CudaNaryMerkleTree(const MerkleTreeConfig &config = MerkleTreeConfig());
-  explicit CudaNaryMerkleTree(const std::vector<FieldElement> &leaves, const MerkleTreeConfig &config = MerkleTreeConfig());
+  // -- construction: the library is brought up on first use; a tree given leaves is built at once
+  explicit CudaNaryMerkleTree(const MerkleTreeConfig &cfg = MerkleTreeConfig());
+  explicit CudaNaryMerkleTree(const std::vector<FieldElement> &leaf_values, const MerkleTreeConfig &cfg = MerkleTreeConfig());
   ~CudaNaryMerkleTree();
   CudaNaryMerkleTree(CudaNaryMerkleTree &&) = default;
   CudaNaryMerkleTree &operator=(CudaNaryMerkleTree &&) = default;
   CudaNaryMerkleTree(const CudaNaryMerkleTree &) = default;
   CudaNaryMerkleTree &operator=(const CudaNaryMerkleTree &) = default;
 
-  bool build_tree(const std::vector<FieldElement> &leaves);
+  // -- GPU build: one upload, every level hashed on the device, one download.  An empty vector clears the tree (true).
+  bool build_tree(const std::vector<FieldElement> &leaf_values);
+  // equal-sized trees are built as one forest pass (cuzk_merkle_build_batch); ragged batches fall back to one build per tree
+  static bool build_batch_trees(const std::vector<std::vector<FieldElement>> &leaf_sets, std::vector<CudaNaryMerkleTree> &out_trees,
+                                const MerkleTreeConfig &cfg = MerkleTreeConfig());
 
-  std::optional<MerkleProof> generate_proof(size_t leaf_index) const;
+  // -- proofs: path[l] = the arity-1 siblings at level l in index order, indices[l] = own slot; nullopt past the last leaf
+  std::optional<MerkleProof> generate_proof(size_t leaf) const;
+  std::vector<MerkleProof> generate_batch_proofs(const std::vector<size_t> &leaf_indices) const;  // invalid indices skipped
+
+  // -- verification on the GPU against this tree's root; the batch form is false for an empty batch or a size mismatch
   bool verify_proof(const MerkleProof &proof, const FieldElement &leaf_value) const;
-
-  std::vector<MerkleProof> generate_batch_proofs(const std::vector<size_t> &indices) const;
   bool verify_batch_proofs(const std::vector<MerkleProof> &proofs, const std::vector<FieldElement> &leaf_values) const;
-  // extension: per-proof verdicts (1 = valid) instead of their conjunction
+  // extension: one verdict per proof (1 = valid) instead of their conjunction
   bool verify_batch_proofs_each(const std::vector<MerkleProof> &proofs, const std::vector<FieldElement> &leaf_values,
-                                std::vector<uint8_t> &results) const;
+                                std::vector<uint8_t> &verdicts) const;
 
-  static bool build_batch_trees(const std::vector<std::vector<FieldElement>> &batch_leaves, std::vector<CudaNaryMerkleTree> &trees,
-                                const MerkleTreeConfig &config = MerkleTreeConfig());
-
+  // -- getters (get_tree_height: the reference's floating-point formula; levels: 0 = padded leaves ... last = root)
   FieldElement get_root_hash() const;
+  size_t get_arity() const { return config_.arity; }
   size_t get_leaf_count() const { return leaf_count_; }
   size_t get_tree_height() const { return tree_height_; }
-  size_t get_arity() const { return config_.arity; }
   const std::vector<FieldElement> &get_leaves() const { return leaves_; }
   const std::vector<std::vector<FieldElement>> &get_tree_levels() const { return tree_levels_; }
-
   void print_tree() const;
 
   // root / leaf count / arity equality with the reference's CPU tree.  A template so that this header does not need the
   // CPU class to be complete; it is instantiated only by callers that have the CPU tree (the reference's tests do).
   template <class CpuTree = NaryMerkleTree>
-  bool compare_with_cpu_tree(const CpuTree &cpu_tree) const {
-    if (get_leaf_count() != cpu_tree.get_leaf_count() || get_arity() != cpu_tree.get_arity()) return false;
-    return get_root_hash() == cpu_tree.get_root_hash();
+  bool compare_with_cpu_tree(const CpuTree &cpu) const {
+    return get_leaf_count() == cpu.get_leaf_count() && get_arity() == cpu.get_arity() && get_root_hash() == cpu.get_root_hash();
   }
 
+  // -- library lifetime and sizing hints
   static bool initialize_cuda();
   static void cleanup_cuda();
   static size_t get_optimal_batch_size();
   static size_t get_max_batch_size();
+
+private:
+  MerkleTreeConfig config_;
+  std::vector<FieldElement> leaves_;
+  std::vector<std::vector<FieldElement>> tree_levels_;  // host copy of every level, like the reference class keeps
+  size_t leaf_count_;
+  size_t tree_height_;
+
+  FieldElement compute_empty_hash(size_t arity) const;
+  void adopt_levels(const std::vector<FieldElement> &leaves, const FieldElement *flat_levels);
 };
 
+// what the benchmark helpers below report (wall clock over host-vector calls)
 struct CudaMerkleTreeStats {
   double total_time_ms;
   double build_time_ms;
@@ -101,11 +104,12 @@ struct CudaMerkleTreeStats {
   size_t arity;
 };
 
-CudaMerkleTreeStats benchmark_cuda_tree_building(size_t num_trees, size_t leaves_per_tree, size_t arity = 2, size_t batch_size = 32);
-CudaMerkleTreeStats benchmark_cuda_proof_generation(size_t num_proofs, size_t leaves_per_tree, size_t arity = 2, size_t batch_size = 256);
-CudaMerkleTreeStats benchmark_cuda_proof_verification(size_t num_proofs, size_t leaves_per_tree, size_t arity = 2, size_t batch_size = 512);
+// leaves FieldElement(seed + tree * n + i) with the reference's seeds; batch_size is accepted and ignored (the library sizes its own launches)
+CudaMerkleTreeStats benchmark_cuda_tree_building(size_t trees, size_t leaves_each, size_t arity = 2, size_t batch_size = 32);
+CudaMerkleTreeStats benchmark_cuda_proof_generation(size_t proofs, size_t leaves_each, size_t arity = 2, size_t batch_size = 256);
+CudaMerkleTreeStats benchmark_cuda_proof_verification(size_t proofs, size_t leaves_each, size_t arity = 2, size_t batch_size = 512);
 // needs the reference's CPU tree at link time; lives in its own source file (merkle_tree_cuda_vs_cpu.cpp)
-CudaMerkleTreeStats benchmark_cuda_vs_cpu_merkle(size_t num_trees, size_t leaves_per_tree, size_t arity = 2, size_t batch_size = 32);
+CudaMerkleTreeStats benchmark_cuda_vs_cpu_merkle(size_t trees, size_t leaves_each, size_t arity = 2, size_t batch_size = 32);
 
 namespace CudaMerkleUtils {
 MerkleTreeConfig get_optimal_config_for_gpu(size_t leaf_count);

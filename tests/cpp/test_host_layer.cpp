@@ -333,8 +333,10 @@ TEST_F(HostMerkle, ProofsVerifyAndCorruptionIsCaught) {
       for (size_t l = 0; l + 1 < levels.size(); ++l) {
         EXPECT_EQ(proofs[i].indices[l], at % arity);
         size_t s = 0;
-        for (size_t c = 0; c < arity; ++c)
-          if (c != at % arity) EXPECT_EQ(proofs[i].path[l][s++], levels[l][at - at % arity + c]);
+        for (size_t c = 0; c < arity; ++c) {
+          if (c == at % arity) continue;
+          EXPECT_EQ(proofs[i].path[l][s++], levels[l][at - at % arity + c]);
+        }
         at /= arity;
       }
     }
