@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 IMAD_PER_PERM = 48_576          # 240 x 164 + 576 x 16 multiply-adds per permutation
 BYTES_PER_PAIR_HASH = 96        # 2 x 32 B in + 32 B out
 N_PAIRS = 1_000_000
+REF_PUBLISHED_PAIR_HASHES_PER_S = 2_145_027   # BASELINE.md section 1 (reference README.md:134, A100)
 METRIC = "poseidon_pair_hashes_per_s"
 UNIT = "hashes/s"
 
@@ -48,7 +49,8 @@ def parse():
 
 def workload_config(args, world):
     return {
-        "workload": f"{args.pairs} Poseidon pair hashes per GPU per step (t=3, R_F=8, R_P=56, BN254 Fr; BASELINE configs[0] 'Large Scale' job on GPU)",
+        "workload": f"{args.pairs} Poseidon pair hashes per GPU per step (t=3, R_F=8, R_P=56, BN254 Fr; BASELINE configs[0] 'Large Scale' job on GPU); "
+                    "the metric's second quantity, Merkle build leaves/s for configs[1..3], is under 'merkle'",
         "pairs_per_gpu": args.pairs,
         "sharding": f"independent slices x{world}, no collective",
         "l2": "4 rotating input/output sets of 96 MB each (384 MB > 126 MB L2)",
@@ -76,6 +78,31 @@ def cpu_reference_run(n_hashes, threads):
     impl.hash_pairs_mt(l, r, threads)
     dt = time.perf_counter() - t0
     return kind, n_hashes / dt, dt
+
+
+def cpu_merkle_baseline(gpu_root):
+    """the reference's own NaryMerkleTree on one host thread -- build over the same
+    50 000 leaves (root compared with the GPU's), then a bounded sample of its generate_proof + verify_proof."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import Ref, have_ref, synth_u64_leaves
+
+    if not have_ref():
+        return {"unavailable": "oracle/_ref/libcuzk_ref.so not built (needs the reference tree at build time)"}
+    ref = Ref()
+    leaves = synth_u64_leaves(3, 50_000)
+    build_ms, root = ref.tree_build_ms(leaves, 2)
+    tree = ref.tree(leaves, 2)
+    sample = 400
+    idx = [(i * 10) % 50_000 for i in range(sample)]
+    t0 = time.perf_counter()
+    proofs = [tree.prove(i) for i in idx]
+    t1 = time.perf_counter()
+    ok = all(tree.verify(leaves[i], sib, pos, root) for i, (sib, pos) in zip(idx, proofs))
+    t2 = time.perf_counter()
+    return {"kind": "reference", "cores": 1, "build_ms": build_ms, "leaves_per_s": 50_000 / (build_ms * 1e-3),
+            "root_equals_gpu": bool((root == gpu_root).all()), "verify_proofs_per_s": sample / (t2 - t1),
+            "prove_proofs_per_s": sample / (t1 - t0), "all_valid": bool(ok),
+            "sample": f"NaryMerkleTree build of the same 50 000 leaves + {sample} of the 5 000 proofs, one host thread"}
 
 
 def reference_arm(args):
@@ -347,6 +374,8 @@ def main():
             vms = a0.elapsed_time(a1) / 5
             merkle["binary_50k"] = {"leaves": 50_000, "arity": 2, "build_ms": ms, "leaves_per_s": 50_000 / (ms * 1e-3),
                                     "verify_5k_ms": vms, "proofs_per_s": 5000 / (vms * 1e-3), "all_valid": bool(res.all())}
+            if world == 1 and not args.no_cpu:
+                merkle["binary_50k"]["cpu_reference"] = cpu_merkle_baseline(levels[-1].cpu().numpy().view(np.uint64).reshape(-1))
             ms, leaves, levels = time_build(1 << 20, 4, 3)
             t = api.CudaNaryMerkleTree(arity=4)
             t.leaf_count, t.levels = 1 << 20, levels
@@ -411,7 +440,9 @@ def main():
             "ms_per_step": ms_per_step,
             "higher_is_better": True,
             "scaling": "weak",
-            "vs_baseline": None,
+            "vs_baseline": value / REF_PUBLISHED_PAIR_HASHES_PER_S,
+            "vs_baseline_note": "BASELINE.md: 2 145 027 pair hashes/s, the reference's CUDA path on an A100 through its 1 M-hash batch-4096 "
+                                "host-vector harness (README.md:134); the same harness shape here is e2e.reference_harness_batch4096",
             "dtype": "u32x8 (256-bit integers, IMAD.WIDE carry chains)",
             "data": "synthetic",
             "config": workload_config(args, world),
