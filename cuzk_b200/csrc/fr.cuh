@@ -15,6 +15,12 @@
 #pragma once
 #include <cstdint>
 
+#ifndef CUZK_KARATSUBA
+#define CUZK_KARATSUBA 0   // 1: one level of Karatsuba for the two full 8x8 products of a multiply (see mul_wide_by_k).
+                           // Bit-exact and 8 % fewer multiplier-pipe cycles, but measured SLOWER on B200 (176.9 vs 185.8 M
+                           // hashes/s): the extra serial carry chains cost more issue slots and latency than the pipe time saved.
+#endif
+
 namespace cuzk {
 
 typedef uint32_t u32;
@@ -273,6 +279,128 @@ __device__ __forceinline__ void mul_wide_8x8(u32 (&r)[16], const u32 (&a)[8], co
   r[15] = addc(e[15], o[15]);
 }
 
+// r[0..7] = a[0..3] * b[0..3] on even/odd lanes (16 multiply-adds)
+__device__ __forceinline__ void mul_wide_4x4(u32 (&r)[8], const u32 *a, const u32 *b) {
+  u32 e[8], o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { e[i] = 0; o[i] = 0; }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if ((i & 1) == 0) {
+      row_chain<2, 0>(e + i, a, b[i]);            // a0, a2 -> even positions i, i+2
+      if (i + 4 < 8) e[i + 4] = addc(0u, 0u);
+      row_chain<2, 0>(o + i + 1, a + 1, b[i]);    // a1, a3 -> odd positions i+1, i+3
+    } else {
+      row_chain<2, 0>(o + i, a, b[i]);
+      if (i + 4 < 8) o[i + 4] = addc(0u, 0u);
+      row_chain<2, 0>(e + i + 1, a + 1, b[i]);
+    }
+  }
+  r[0] = e[0];
+  r[1] = add_cc(e[1], o[1]);
+#pragma unroll
+  for (int i = 2; i < 7; ++i) r[i] = addc_cc(e[i], o[i]);
+  r[7] = addc(e[7], o[7]);
+}
+
+// ---- one level of Karatsuba over the 128-bit halves: three 4x4 products (48 multiply-adds) instead of 64 -------------
+// The 32x32->64 multiplier is the kernel's bound and the ALU has slack, so ~45 extra carry-chain adds per product are a
+// good trade for 16 multiply-adds.  Exact for any operands:
+//   a = a0 + a1 W2, b = b0 + b1 W2 (W2 = 2^128):  a b = z0 + (zm - z0 - z2) W2 + z2 W2^2,
+//   z0 = a0 b0, z2 = a1 b1, zm = (a0 + a1)(b0 + b1) = as bs + ca bs W2 + cb as W2 + ca cb W2^2   (ca, cb = the sums' carry bits)
+#define CUZK_KS0 0xc8794629u   // k0 + k1 for k = 2^256 mod p (no carry out: 0x4506ee573968ac591304d78bc8794629)
+#define CUZK_KS1 0x1304d78bu
+#define CUZK_KS2 0x3968ac59u
+#define CUZK_KS3 0x4506ee57u
+
+// shared tail: r = z0 + (zm9 - z0 - z2) * 2^128 + z2 * 2^256, zm9 = zm[0..7] + zm8 * 2^256
+__device__ __forceinline__ void karatsuba_combine(u32 (&r)[16], const u32 (&z0)[8], const u32 (&z2)[8], u32 (&zm)[8], u32 zm8) {
+  u32 s[9];
+  s[0] = add_cc(z0[0], z2[0]);
+#pragma unroll
+  for (int i = 1; i < 8; ++i) s[i] = addc_cc(z0[i], z2[i]);
+  s[8] = addc(0u, 0u);
+  u32 z1[9];
+  z1[0] = sub_cc(zm[0], s[0]);
+#pragma unroll
+  for (int i = 1; i < 8; ++i) z1[i] = subc_cc(zm[i], s[i]);
+  z1[8] = subc(zm8, s[8]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r[i] = z0[i];
+  r[4] = add_cc(z0[4], z1[0]);
+#pragma unroll
+  for (int i = 1; i < 4; ++i) r[4 + i] = addc_cc(z0[4 + i], z1[i]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r[8 + i] = addc_cc(z2[i], z1[4 + i]);
+  r[12] = addc_cc(z2[4], z1[8]);
+  r[13] = addc_cc(z2[5], 0u);
+  r[14] = addc_cc(z2[6], 0u);
+  r[15] = addc(z2[7], 0u);
+}
+
+// r[0..15] = a * k for the constant k = 2^256 mod p
+__device__ __forceinline__ void mul_wide_by_k(u32 (&r)[16], const u32 (&a)[8]) {
+  const u32 klo[4] = {CUZK_K0, CUZK_K1, CUZK_K2, CUZK_K3}, khi[4] = {CUZK_K4, CUZK_K5, CUZK_K6, CUZK_K7};
+  const u32 ks[4] = {CUZK_KS0, CUZK_KS1, CUZK_KS2, CUZK_KS3};
+  u32 z0[8], z2[8], zm[8], as[4];
+  mul_wide_4x4(z0, a, klo);
+  mul_wide_4x4(z2, a + 4, khi);
+  as[0] = add_cc(a[0], a[4]);
+  as[1] = addc_cc(a[1], a[5]);
+  as[2] = addc_cc(a[2], a[6]);
+  as[3] = addc_cc(a[3], a[7]);
+  const u32 ca = addc(0u, 0u);
+  mul_wide_4x4(zm, as, ks);
+  // zm += ca * ks * 2^128  (ks has no carry bit of its own)
+  u32 zm8;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.u32 p, %5, 0;\n\t"
+      "mov.u32 %4, 0;\n\t"
+      "@p add.cc.u32 %0, %0, %6;\n\t"
+      "@p addc.cc.u32 %1, %1, %7;\n\t"
+      "@p addc.cc.u32 %2, %2, %8;\n\t"
+      "@p addc.cc.u32 %3, %3, %9;\n\t"
+      "@p addc.u32 %4, %4, 0;\n\t"
+      "}"
+      : "+r"(zm[4]), "+r"(zm[5]), "+r"(zm[6]), "+r"(zm[7]), "=r"(zm8)
+      : "r"(ca), "n"(CUZK_KS0), "n"(CUZK_KS1), "n"(CUZK_KS2), "n"(CUZK_KS3));
+  karatsuba_combine(r, z0, z2, zm, zm8);
+}
+
+// r[0..15] = a * b for two register operands
+__device__ __forceinline__ void mul_wide_8x8_karatsuba(u32 (&r)[16], const u32 (&a)[8], const u32 (&b)[8]) {
+  u32 z0[8], z2[8], zm[8], as[4], bs[4];
+  mul_wide_4x4(z0, a, b);
+  mul_wide_4x4(z2, a + 4, b + 4);
+  as[0] = add_cc(a[0], a[4]);
+  as[1] = addc_cc(a[1], a[5]);
+  as[2] = addc_cc(a[2], a[6]);
+  as[3] = addc_cc(a[3], a[7]);
+  const u32 ca = addc(0u, 0u);
+  bs[0] = add_cc(b[0], b[4]);
+  bs[1] = addc_cc(b[1], b[5]);
+  bs[2] = addc_cc(b[2], b[6]);
+  bs[3] = addc_cc(b[3], b[7]);
+  const u32 cb = addc(0u, 0u);
+  mul_wide_4x4(zm, as, bs);
+  // zm9 = zm + (ca ? bs : 0) * 2^128 + (cb ? as : 0) * 2^128 + (ca & cb) * 2^256
+  const u32 ma = 0u - ca, mb = 0u - cb;
+  u32 zm8 = ca & cb;
+  zm[4] = add_cc(zm[4], bs[0] & ma);
+  zm[5] = addc_cc(zm[5], bs[1] & ma);
+  zm[6] = addc_cc(zm[6], bs[2] & ma);
+  zm[7] = addc_cc(zm[7], bs[3] & ma);
+  zm8 = addc(zm8, 0u);
+  zm[4] = add_cc(zm[4], as[0] & mb);
+  zm[5] = addc_cc(zm[5], as[1] & mb);
+  zm[6] = addc_cc(zm[6], as[2] & mb);
+  zm[7] = addc_cc(zm[7], as[3] & mb);
+  zm8 = addc(zm8, 0u);
+  karatsuba_combine(r, z0, z2, zm, zm8);
+}
+
 // t[0..7] = (t + a * b) mod 2^256   (low half only; 28 wide + 8 low products)
 __device__ __forceinline__ void mad_low_8x8(u32 (&t)[8], const u32 (&a)[8], const u32 (&b)[8]) {
   u32 e[8], o[8];
@@ -317,7 +445,12 @@ __device__ __forceinline__ void fr_reduce_512(u32 (&r)[8], const u32 (&prod)[16]
 #pragma unroll
   for (int i = 0; i < 8; ++i) high[i] = prod[8 + i];
   u32 m1[16];
+#if CUZK_KARATSUBA
+  if (EXACT) mul_wide_8x8(m1, high, kk);   // the exact path stays on the schoolbook product: an independent evaluation
+  else mul_wide_by_k(m1, high);
+#else
   mul_wide_8x8(m1, high, kk);
+#endif
   u32 t[8], mh[8];
   u32 mh_or = 0;
 #pragma unroll
@@ -340,7 +473,12 @@ __device__ __forceinline__ void fr_reduce_512(u32 (&r)[8], const u32 (&prod)[16]
 template <bool EXACT>
 __device__ __forceinline__ void fr_mul_t(u32 (&r)[8], const u32 (&a)[8], const u32 (&b)[8], u32 &unc) {
   u32 prod[16];
+#if CUZK_KARATSUBA
+  if (EXACT) mul_wide_8x8(prod, a, b);
+  else mul_wide_8x8_karatsuba(prod, a, b);
+#else
   mul_wide_8x8(prod, a, b);
+#endif
   fr_reduce_512<EXACT>(r, prod, unc);
 }
 __device__ __forceinline__ void fr_mul(u32 (&r)[8], const u32 (&a)[8], const u32 (&b)[8]) {
