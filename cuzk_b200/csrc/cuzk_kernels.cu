@@ -637,8 +637,8 @@ int merkle_build_dev(const uint64_t *leaves, size_t n, unsigned arity, uint64_t 
 }
 
 // roots of `count` consecutive subtrees of arity^height (virtual) leaves whose first n leaves are in memory
-int subtree_roots_dev(const uint64_t *leaves, size_t n, unsigned arity, unsigned height, size_t count, uint64_t *roots_out,
-                      cudaStream_t st) {
+int subtree_roots_one_stream(const uint64_t *leaves, size_t n, unsigned arity, unsigned height, size_t count, uint64_t *roots_out,
+                             cudaStream_t st) {
   int rc = ensure_padding(arity);
   if (rc) return rc;
   if ((int)height + 1 >= g_pad_levels[arity]) return fail(CUZK_ERR_INVALID, "subtree too tall");
@@ -686,6 +686,59 @@ int subtree_roots_dev(const uint64_t *leaves, size_t n, unsigned arity, unsigned
   }
   release();
   return CUZK_OK;
+}
+
+// The upper levels of a subtree are narrow: a level with fewer nodes than the chip has thread slots takes one node-hash
+// latency (about 0.18 ms per permutation) however few nodes it has.  With several subtrees per call, groups of subtrees run
+// on separate internal streams, so the narrow levels of one group hide behind the wide levels of the next.
+constexpr int kSubtreeStreams = 4;
+cudaStream_t g_sub_stream[kSubtreeStreams] = {};
+cudaEvent_t g_sub_fork = nullptr, g_sub_join[kSubtreeStreams] = {};
+std::mutex g_sub_mu;   // the internal streams and events are shared by all callers
+
+int subtree_streams_start() {
+  if (g_sub_fork) return CUZK_OK;
+  for (int i = 0; i < kSubtreeStreams; ++i) {
+    CK(cudaStreamCreateWithFlags(&g_sub_stream[i], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&g_sub_join[i], cudaEventDisableTiming));
+  }
+  CK(cudaEventCreateWithFlags(&g_sub_fork, cudaEventDisableTiming));
+  return CUZK_OK;
+}
+void subtree_streams_stop() {
+  for (int i = 0; i < kSubtreeStreams; ++i) {
+    if (g_sub_stream[i]) cudaStreamDestroy(g_sub_stream[i]);
+    if (g_sub_join[i]) cudaEventDestroy(g_sub_join[i]);
+    g_sub_stream[i] = nullptr;
+    g_sub_join[i] = nullptr;
+  }
+  if (g_sub_fork) cudaEventDestroy(g_sub_fork);
+  g_sub_fork = nullptr;
+}
+
+int subtree_roots_dev(const uint64_t *leaves, size_t n, unsigned arity, unsigned height, size_t count, uint64_t *roots_out,
+                      cudaStream_t st) {
+  size_t span = 1;
+  for (unsigned i = 0; i < height; ++i) span *= arity;
+  const size_t real_subtrees = ceil_div(n, span);   // subtrees with at least one real leaf; the rest are padding constants
+  const size_t groups = std::min<size_t>(real_subtrees, kSubtreeStreams);
+  if (height < 3 || groups < 2 || g_sub_fork == nullptr) return subtree_roots_one_stream(leaves, n, arity, height, count, roots_out, st);
+  std::lock_guard<std::mutex> lk(g_sub_mu);
+  CK(cudaEventRecord(g_sub_fork, st));
+  int rc = CUZK_OK;
+  for (size_t g = 0; g < groups; ++g) {
+    const size_t lo = real_subtrees * g / groups;
+    const size_t hi = (g + 1 == groups) ? count : real_subtrees * (g + 1) / groups;   // the last group also writes the padding roots
+    const size_t first_leaf = lo * span;
+    const size_t n_g = std::min(n - first_leaf, (hi - lo) * span);
+    cudaStream_t sg = g_sub_stream[g];
+    CK(cudaStreamWaitEvent(sg, g_sub_fork, 0));
+    const int r = subtree_roots_one_stream(leaves + 4 * first_leaf, n_g, arity, height, hi - lo, roots_out + 4 * lo, sg);
+    if (r && !rc) rc = r;
+    CK(cudaEventRecord(g_sub_join[g], sg));
+    CK(cudaStreamWaitEvent(st, g_sub_join[g], 0));
+  }
+  return rc;
 }
 
 }  // namespace
@@ -773,6 +826,7 @@ int cuzk_init(int device) {
   static const uint64_t m[9] = {7, 23, 8, 26, 5, 4, 15, 20, 9};
   memset(g_host_mds, 0, sizeof g_host_mds);
   for (int i = 0; i < 9; ++i) g_host_mds[4 * i] = m[i];
+  if ((rc = subtree_streams_start())) return rc;
   g_device = device;
   g_refcount = 1;
   return CUZK_OK;
@@ -791,6 +845,7 @@ int cuzk_shutdown(void) {
     {
       std::lock_guard<std::mutex> lk2(g_hp_mu);
       hp_stop();
+      subtree_streams_stop();
     }
     g_device = -1;
   }
