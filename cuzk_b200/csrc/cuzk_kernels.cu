@@ -367,8 +367,9 @@ __global__ void merkle_prove_kernel(const uint4 *__restrict__ levels, size_t n, 
 // verify: one thread per proof.  batch_verify_proofs_kernel : merkle_tree_cuda.cu:67-118 / verify_proof : merkle_tree.cpp:214-254
 __global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) merkle_verify_kernel(const uint4 *__restrict__ leaves, const uint4 *__restrict__ sib,
                                                                 const u32 *__restrict__ pos, int nlv, int arity,
-                                                                const uint4 *__restrict__ root, uint8_t *__restrict__ results,
-                                                                size_t num_proofs) {
+                                                                const uint4 *__restrict__ root, uint4 root_lo, uint4 root_hi,
+                                                                uint8_t *__restrict__ results, size_t num_proofs) {
+  // the expected root comes from device memory (`root`) or, for host-buffer calls, by value (root == nullptr)
   size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= num_proofs) return;
   u32 cur[8];
@@ -394,7 +395,12 @@ __global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) merkle_verify_kernel(
   }
   if (ok) {
     u32 rt[8];
-    load_fr(rt, root);
+    if (root) {
+      load_fr(rt, root);
+    } else {
+      rt[0] = root_lo.x; rt[1] = root_lo.y; rt[2] = root_lo.z; rt[3] = root_lo.w;
+      rt[4] = root_hi.x; rt[5] = root_hi.y; rt[6] = root_hi.z; rt[7] = root_hi.w;
+    }
     u32 diff = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) diff |= rt[w] ^ cur[w];
@@ -1120,15 +1126,13 @@ int cuzk_merkle_verify_batch(const uint64_t *leaf_values, const uint64_t *siblin
   if (mem == CUZK_MEM_DEVICE) {
     merkle_verify_kernel<<<grid_for(num_proofs, kBlock), kBlock, 0, st>>>(reinterpret_cast<const uint4 *>(leaf_values),
                                                                          reinterpret_cast<const uint4 *>(siblings), positions, (int)levels,
-                                                                         (int)arity, reinterpret_cast<const uint4 *>(root), results_out, num_proofs);
+                                                                         (int)arity, reinterpret_cast<const uint4 *>(root), uint4{}, uint4{},
+                                                                         results_out, num_proofs);
     return check_launch("merkle_verify_kernel");
   }
-  void *droot;
-  {
-    std::lock_guard<std::mutex> lk(g_hp_mu);
-    if ((rc = ws_get(4, 32, &droot))) return rc;
-    CK(cudaMemcpy(droot, root, 32, cudaMemcpyHostToDevice));
-  }
+  uint4 root_lo, root_hi;   // host-buffer call: the 32-byte root travels as a kernel argument
+  memcpy(&root_lo, root, 16);
+  memcpy(&root_hi, root + 2, 16);
   const void *ins[3] = {leaf_values, siblings, positions};
   const size_t in_bytes[3] = {32, levels * (arity - 1) * 32, levels * 4};
   // proofs are independent: chunk them like hashes (each costs levels x ceil(arity/2) permutations)
@@ -1136,7 +1140,7 @@ int cuzk_merkle_verify_batch(const uint64_t *leaf_values, const uint64_t *siblin
                        [&](cudaStream_t s2, void **d_in, void *d_out, size_t m) {
                          merkle_verify_kernel<<<grid_for(m, kBlock), kBlock, 0, s2>>>(
                              static_cast<const uint4 *>(d_in[0]), static_cast<const uint4 *>(d_in[1]), static_cast<const u32 *>(d_in[2]),
-                             (int)levels, (int)arity, static_cast<const uint4 *>(droot), static_cast<uint8_t *>(d_out), m);
+                             (int)levels, (int)arity, nullptr, root_lo, root_hi, static_cast<uint8_t *>(d_out), m);
                          return check_launch("merkle_verify_kernel");
                        });
 }
