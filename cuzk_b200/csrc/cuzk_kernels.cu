@@ -179,6 +179,31 @@ __global__ void __launch_bounds__(kBlock) debug_mds_kernel(uint4 *states, size_t
   store_fr(states + 6 * i + 4, s2);
 }
 
+// test hook: the FAST-PATH field operations on their own, with the "undecided comparison" flag they raise.
+// op 0 = reduce (any 256-bit a), 1 = multiply, 2 = square, 3 = power5.  Soundness property checked by the tests:
+// flags[i] == 0  =>  out[i] equals the reference operation bit for bit.
+__global__ void __launch_bounds__(kBlock) debug_fast_ops_kernel(int op, const uint4 *__restrict__ a, const uint4 *__restrict__ b,
+                                                                 uint4 *__restrict__ out, u32 *__restrict__ flags, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u32 x[8], y[8], r[8], unc = 0;
+  load_fr(x, a + 2 * i);
+  if (op == 0) {
+#pragma unroll
+    for (int w = 0; w < 8; ++w) r[w] = x[w];
+    fr_reduce_fast(r, unc);
+  } else if (op == 1) {
+    load_fr(y, b + 2 * i);
+    fr_mul_t<false>(r, x, y, unc);
+  } else if (op == 2) {
+    fr_sqr_t<false>(r, x, unc);
+  } else {
+    fr_pow5_t<false>(r, x, unc);
+  }
+  store_fr(out + 2 * i, r);
+  flags[i] = unc;
+}
+
 // generic sponge: out[i] = sponge(in[i*width ..], ds)
 __global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) sponge_kernel(const uint4 *__restrict__ in, int width, u32 ds_lo, u32 ds_hi,
                                                          uint4 *__restrict__ out, size_t n) {
@@ -938,6 +963,17 @@ int cuzk_debug_mds_layer(uint64_t *states, size_t n, int mode, void *stream) {
   if (n == 0) return CUZK_OK;
   debug_mds_kernel<<<grid_for(n, kBlock), kBlock, 0, S(stream)>>>(reinterpret_cast<uint4 *>(states), n, mode);
   return check_launch("debug_mds_kernel");
+}
+
+int cuzk_debug_fast_ops(int op, const uint64_t *a, const uint64_t *b, uint64_t *out, uint32_t *flags, size_t n, void *stream) {
+  int rc = require_init();
+  if (rc) return rc;
+  if (op < 0 || op > 3) return fail(CUZK_ERR_INVALID, "unknown fast op");
+  if (n == 0) return CUZK_OK;
+  if (!a || !out || !flags || (op == 1 && !b)) return fail(CUZK_ERR_INVALID, "null pointer");
+  debug_fast_ops_kernel<<<grid_for(n, kBlock), kBlock, 0, S(stream)>>>(op, reinterpret_cast<const uint4 *>(a), reinterpret_cast<const uint4 *>(b),
+                                                                      reinterpret_cast<uint4 *>(out), flags, n);
+  return check_launch("debug_fast_ops_kernel");
 }
 
 int cuzk_poseidon_sponge(const uint64_t *in, size_t width, uint64_t ds, uint64_t *out, size_t n, int mem, void *stream) {

@@ -121,6 +121,7 @@ _SIGS = {
     "cuzk_synth_u64_leaves": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_void_p]),
     "cuzk_debug_fallback_count": (C.c_uint64, []),
     "cuzk_debug_set_fuse": (C.c_int, [C.c_int]),
+    "cuzk_debug_fast_ops": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "cuzk_debug_mds_layer": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "cuzk_imad_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
 }

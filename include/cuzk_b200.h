@@ -197,6 +197,11 @@ int cuzk_debug_set_fuse(int mode);
  * path met a comparison its top-word test could not decide (about 1e-6 per permutation on random data); a blocking read */
 uint64_t cuzk_debug_fallback_count(void);
 
+/* test hook (device pointers): the fast-path field operations on their own -- op 0 = reduce(a), 1 = multiply(a, b),
+ * 2 = square(a), 3 = power5(a) -- with the flag each raises when a top-word comparison was undecided.  The property the
+ * kernels rely on, and the tests check on crafted boundary values: flags[i] == 0 implies out[i] is the reference result. */
+int cuzk_debug_fast_ops(int op, const uint64_t *a, const uint64_t *b, uint64_t *out, uint32_t *flags, size_t n, void *stream);
+
 /* integer-multiply pipe microbenchmark: runs `iters` rounds of dependent-free IMAD.WIDE chains on the whole
  * chip and returns measured 32x32->64 multiply-adds per second (the roofline denominator); variant selects
  * 0 = IMAD.WIDE.U32, 1 = IMAD (lo), 2 = IMAD.HI, 3 = IMAD.WIDE.U32.X carry chains, 4 = IADD3.X carry chains,

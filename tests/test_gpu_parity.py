@@ -531,3 +531,90 @@ def test_fused_and_per_level_builds_agree_with_oracle(gpu, oracle, mode):
                 assert (to_host(root)[0] == want[-1][0]).all(), (mode, arity, n)
     finally:
         L.cuzk_debug_set_fuse(old)
+
+
+def test_fast_path_flags_are_sound(gpu, oracle):
+    """The fast-path reduce / multiply / square / power5 may leave a comparison undecided, and must then say so: whenever the
+    flag is clear the result equals the reference operation.  Checked on values crafted around every multiple of p (top words
+    equal, one above, one below; low words all-ones / zero / random) and on random operands; the crafted reduce inputs must
+    also actually raise the flag in the undecidable cases (otherwise this test would be vacuous)."""
+    import torch
+
+    from cuzk_b200 import lib
+    from oracle_lib import P_INT, ints_to_array
+
+    L = lib.get_lib()
+    rng = np.random.default_rng(77)
+    W = 1 << 256
+    vals = []
+    for m in range(0, 6):
+        mp = m * P_INT
+        top = mp >> 224
+        for dt in (-1, 0, 1):
+            t = top + dt
+            if t < 0 or t >= (1 << 32):
+                continue
+            for low in (0, (1 << 224) - 1, mp & ((1 << 224) - 1), (mp & ((1 << 224) - 1)) - 1, (mp & ((1 << 224) - 1)) + 1,
+                        int(rng.integers(0, 2**62)) << 160):
+                vals.append(((t << 224) | (low & ((1 << 224) - 1))) % W)
+        for d in (-2, -1, 0, 1, 2):
+            if 0 <= mp + d < W:
+                vals.append(mp + d)
+    vals += [0, 1, W - 1, W - 2]
+    crafted = ints_to_array(vals)
+
+    def run(op, a, b=None):
+        da, db = to_dev(a), (to_dev(b) if b is not None else None)
+        out = torch.empty_like(da)
+        fl = torch.empty(a.shape[0], dtype=torch.int32, device="cuda")
+        L.check(L.cuzk_debug_fast_ops(op, da.data_ptr(), db.data_ptr() if db is not None else None, out.data_ptr(), fl.data_ptr(),
+                                      a.shape[0], None), "debug_fast_ops")
+        return to_host(out), fl.cpu().numpy()
+
+    # reduce: oracle add(x, 0) = reduce(x)
+    x = np.concatenate([crafted, rnd(rng, 200_000, False)])
+    got, fl = run(0, x)
+    want = oracle.batch_fr("add", x, np.zeros_like(x))
+    ok = (got == want).all(axis=1)
+    assert (ok | (fl != 0)).all(), "a fast reduce was wrong without raising its flag"
+    assert fl[: crafted.shape[0]].any() and (~ok[: crafted.shape[0]]).any(), "crafted inputs did not reach the undecidable case"
+    assert fl[crafted.shape[0] :].mean() < 1e-3
+    # multiply / square / power5 on random canonical, random 256-bit, small, and crafted operands
+    pools = [rnd(rng, 150_000, True), rnd(rng, 50_000, False), synth_u64_leaves(1, 20_000), crafted]
+    a = np.concatenate(pools)
+    b = np.concatenate([rnd(rng, 150_000, True), rnd(rng, 50_000, False), synth_u64_leaves(2, 20_000), crafted[::-1].copy()])
+    for op, name, args in ((1, "mul", (a, b)), (2, "sqr", (a,)), (3, "pow5", (a,))):
+        got, fl = run(op, *args)
+        want = oracle.batch_fr(name, *args)
+        ok = (got == want).all(axis=1)
+        assert (ok | (fl != 0)).all(), f"fast {name} wrong without a flag at {np.nonzero(~ok & (fl == 0))[0][:5]}"
+        assert fl.mean() < 1e-2, name
+
+
+def test_million_pair_hashes_compared_in_full(gpu, oracle):
+    """BASELINE configs[0] size: 1,000,000 pair hashes (the bench's seeded stream), EVERY output compared with the CPU
+    implementation running on all host threads -- not a sample, so that a rare fast-path slip could not hide."""
+    import os
+
+    import torch
+
+    from cuzk_b200 import lib
+
+    L = lib.get_lib()
+    n = 1_000_000
+    dl = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+    dr = torch.empty_like(dl)
+    out = torch.empty_like(dl)
+    L.check(L.cuzk_synth_elements(dl.data_ptr(), n, 1, 0, 1, None), "synth")
+    L.check(L.cuzk_synth_elements(dr.data_ptr(), n, 2, 0, 1, None), "synth")
+    before = L.cuzk_debug_fallback_count()
+    L.check(L.cuzk_poseidon_hash_pairs(dl.data_ptr(), dr.data_ptr(), out.data_ptr(), n, 0, None), "pairs")
+    got = to_host(out)
+    taken = L.cuzk_debug_fallback_count() - before
+    l, r = synth_elements(1, n), synth_elements(2, n)
+    assert (to_host(dl[:1000]) == l[:1000]).all()
+    threads = max(1, len(os.sched_getaffinity(0)))
+    want = oracle.hash_pairs_mt(l, r, threads)
+    bad = np.nonzero((got != want).any(axis=1))[0]
+    assert bad.size == 0, (bad[:5], taken)
+    assert taken < 1000, f"{taken} of 1e6 hashes took the exact fallback: the fast path should decide almost always"
