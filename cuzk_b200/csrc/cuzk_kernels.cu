@@ -36,9 +36,11 @@ uint64_t g_host_mds[9 * 4];
 
 // padding constants E_l per arity: E_0 = empty_hash(arity), E_{l+1} = hash_multiple(arity x E_l)
 constexpr int kMaxPadLevels = 41;
-uint64_t *g_d_pad[9] = {nullptr};           // device, kMaxPadLevels x 4 u64 per arity
-uint64_t g_h_pad[9][kMaxPadLevels][4];      // host copy
-int g_pad_levels[9] = {0};
+uint64_t *g_d_pad[9] = {nullptr};           // device, kMaxPadLevels x 4 u64 per arity (per cuzk_init .. cuzk_shutdown)
+uint64_t g_h_pad[9][kMaxPadLevels][4];      // host copy; constants of the hash function, kept for the life of the process
+int g_h_pad_levels[9] = {0};                // how many levels the host copy holds
+int g_pad_levels[9] = {0};                  // how many levels the device copy holds
+std::mutex g_pad_mu;
 
 int fail(int code, const std::string &msg) {
   g_err = msg;
@@ -216,11 +218,13 @@ __global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) sponge_kernel(const u
 }
 
 // padding chain for one arity: pad[0] = hash_multiple(arity zeros), pad[l+1] = hash_multiple(arity x pad[l])
-__global__ void padding_chain_kernel(uint4 *pad, int arity, int levels) {
+// computes levels [start, end); level start-1 must already be in pad[] when start > 0
+__global__ void padding_chain_kernel(uint4 *pad, int arity, int start, int end) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   u32 cur[8];
-  set_small(cur, 0);
-  for (int l = 0; l < levels; ++l) {
+  if (start > 0) load_fr_plain(cur, pad + 2 * (start - 1));
+  else set_small(cur, 0);
+  for (int l = start; l < end; ++l) {
     u32 outv[8];
     const u32(&c)[8] = cur;
     sponge_n(outv, 3u, arity, [&](u32(&x)[8], int) {
@@ -568,19 +572,31 @@ int host_pipeline(size_t n, size_t chunk, int nin, const void *const *in, const 
   return CUZK_OK;
 }
 
-int ensure_padding(unsigned arity) {
-  if (g_d_pad[arity]) return CUZK_OK;
-  // enough levels for arity^L <= 2^40 leaves, plus the root level
-  int levels = 2;
-  for (double cap = arity; cap < 1.1e12 && levels < kMaxPadLevels; cap *= arity) ++levels;
-  uint64_t *d = nullptr;
-  CK(cudaMalloc(&d, (size_t)kMaxPadLevels * 32));
-  padding_chain_kernel<<<1, 32>>>(reinterpret_cast<uint4 *>(d), (int)arity, levels);
+// makes the padding constants E_0 .. E_{need-1} of `arity` available on the device.  The chain is sequential (one thread,
+// ceil(arity/2) permutations per level), so it is computed only as far as trees need it, extended on demand, and the
+// values -- constants of the hash function -- are cached on the host across cuzk_shutdown / cuzk_init cycles.
+int ensure_padding(unsigned arity, int need = 2) {
+  if (need > kMaxPadLevels) return fail(CUZK_ERR_INVALID, "tree too tall");
+  std::lock_guard<std::mutex> lk(g_pad_mu);
+  if (g_d_pad[arity] && g_pad_levels[arity] >= need) return CUZK_OK;
+  if (!g_d_pad[arity]) {
+    uint64_t *d = nullptr;
+    CK(cudaMalloc(&d, (size_t)kMaxPadLevels * 32));
+    g_d_pad[arity] = d;
+    g_pad_levels[arity] = 0;
+  }
+  uint64_t *d = g_d_pad[arity];
+  if (g_pad_levels[arity] < g_h_pad_levels[arity]) {   // bring the device copy up to what the host already knows
+    CK(cudaMemcpy(d, g_h_pad[arity], (size_t)g_h_pad_levels[arity] * 32, cudaMemcpyHostToDevice));
+    g_pad_levels[arity] = g_h_pad_levels[arity];
+  }
+  if (g_pad_levels[arity] >= need) return CUZK_OK;
+  const int start = g_pad_levels[arity], end = std::min(kMaxPadLevels, std::max(need, start + 4));
+  padding_chain_kernel<<<1, 32>>>(reinterpret_cast<uint4 *>(d), (int)arity, start, end);
   int rc = check_launch("padding_chain_kernel");
   if (rc) return rc;
-  CK(cudaMemcpy(g_h_pad[arity], d, (size_t)levels * 32, cudaMemcpyDeviceToHost));
-  g_pad_levels[arity] = levels;
-  g_d_pad[arity] = d;
+  CK(cudaMemcpy(g_h_pad[arity][start], d + 4 * start, (size_t)(end - start) * 32, cudaMemcpyDeviceToHost));
+  g_pad_levels[arity] = g_h_pad_levels[arity] = end;
   return CUZK_OK;
 }
 
@@ -635,11 +651,10 @@ int launch_fused2(const uint4 *in, uint4 *mid, uint4 *out, size_t in_real, size_
 // builds `ntrees` trees of n leaves each in one pass: one launch per level (or per two levels) for the whole forest.
 // leaves: ntrees x n elements; levels_out: ntrees flat level-major trees of total_nodes(n) elements each.
 int merkle_build_dev(const uint64_t *leaves, size_t n, unsigned arity, uint64_t *levels_out, cudaStream_t st, size_t ntrees = 1) {
-  int rc = ensure_padding(arity);
+  int rc = ensure_padding(arity, (int)cuzk_merkle_num_levels(n, arity) + 1);
   if (rc) return rc;
   const uint4 *pad = reinterpret_cast<const uint4 *>(g_d_pad[arity]);
   size_t padded = cuzk_merkle_padded_leaves(n, arity);
-  if ((int)cuzk_merkle_num_levels(n, arity) >= g_pad_levels[arity]) return fail(CUZK_ERR_INVALID, "tree too tall");
   const size_t stride = cuzk_merkle_total_nodes(n, arity);
   uint4 *cur = reinterpret_cast<uint4 *>(levels_out);
   merkle_pad_leaves_kernel<<<grid_for(padded * ntrees, 256), 256, 0, st>>>(reinterpret_cast<const uint4 *>(leaves), n, padded, pad, cur,
@@ -670,9 +685,8 @@ int merkle_build_dev(const uint64_t *leaves, size_t n, unsigned arity, uint64_t 
 // roots of `count` consecutive subtrees of arity^height (virtual) leaves whose first n leaves are in memory
 int subtree_roots_one_stream(const uint64_t *leaves, size_t n, unsigned arity, unsigned height, size_t count, uint64_t *roots_out,
                              cudaStream_t st) {
-  int rc = ensure_padding(arity);
+  int rc = ensure_padding(arity, (int)height + 2);
   if (rc) return rc;
-  if ((int)height + 1 >= g_pad_levels[arity]) return fail(CUZK_ERR_INVALID, "subtree too tall");
   const uint4 *pad = reinterpret_cast<const uint4 *>(g_d_pad[arity]);
   if (height == 0) {
     merkle_pad_leaves_kernel<<<grid_for(count, 256), 256, 0, st>>>(reinterpret_cast<const uint4 *>(leaves), n, count, pad,
@@ -1028,8 +1042,8 @@ int cuzk_merkle_padding_root(unsigned arity, unsigned height, uint64_t out[4]) {
   int rc = require_init();
   if (rc) return rc;
   if ((rc = check_arity(arity))) return rc;
-  if ((rc = ensure_padding(arity))) return rc;
-  if ((int)height >= g_pad_levels[arity]) return fail(CUZK_ERR_INVALID, "padding level too high");
+  if (height >= (unsigned)kMaxPadLevels) return fail(CUZK_ERR_INVALID, "padding level too high");
+  if ((rc = ensure_padding(arity, (int)height + 1))) return rc;
   memcpy(out, g_h_pad[arity][height], 32);
   return CUZK_OK;
 }
