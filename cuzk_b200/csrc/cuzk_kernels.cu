@@ -10,9 +10,11 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/cuzk_b200.h"
@@ -525,6 +527,7 @@ void hp_stop() {
   }
   g_hp.ready = false;
 }
+void pin_stop();
 
 int require_init() {
   if (g_refcount <= 0) return fail(CUZK_ERR_CUDA, "cuzk_b200: library not initialised (call cuzk_init)");
@@ -538,6 +541,182 @@ int check_launch(const char *what) {
   return CUZK_OK;
 }
 
+// ---- parallel host copies for pageable caller memory ----------------------------------------------------------------
+// cudaMemcpyAsync on pageable memory (a std::vector, which is what the reference's API hands us) is staged by the driver
+// through one thread at well under PCIe speed.  For such buffers the pipeline below stages through its own pinned bounce
+// buffers and fills / drains them with a few worker threads, so the DMA runs at pinned-memory speed while the copy of the
+// next chunk overlaps the kernel of the current one.
+class CopyPool {
+ public:
+  void copy(void *dst, const void *src, size_t bytes) {
+    if (bytes < (1u << 20) || !start()) {
+      memcpy(dst, src, bytes);
+      return;
+    }
+    const int parts = (int)workers_.size() + 1;
+    const size_t slice = ((bytes / parts) + 4095) & ~(size_t)4095;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      dst_ = static_cast<char *>(dst);
+      src_ = static_cast<const char *>(src);
+      bytes_ = bytes;
+      slice_ = slice;
+      pending_ = (int)workers_.size();
+      ++generation_;
+    }
+    cv_.notify_all();
+    run_slice(parts - 1);   // the caller takes the last slice
+    std::unique_lock<std::mutex> lk(mu_);
+    done_cv_.wait(lk, [&] { return pending_ == 0; });
+  }
+  ~CopyPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto &t : workers_) t.join();
+  }
+
+ private:
+  bool start() {
+    if (started_) return !workers_.empty();
+    started_ = true;
+    unsigned hw = std::thread::hardware_concurrency();
+    int n = (int)std::min<unsigned>(3, hw > 2 ? hw / 2 - 1 : 0);   // three helpers + the caller saturate one socket's copy rate
+    for (int i = 0; i < n; ++i) workers_.emplace_back([this, i] { loop(i); });
+    return !workers_.empty();
+  }
+  void run_slice(int part) {
+    const size_t off = slice_ * (size_t)part;
+    if (off < bytes_) memcpy(dst_ + off, src_ + off, std::min(slice_, bytes_ - off));
+  }
+  void loop(int idx) {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
+        if (stop_) return;
+        seen = generation_;
+      }
+      run_slice(idx);
+      std::lock_guard<std::mutex> lk(mu_);
+      if (--pending_ == 0) done_cv_.notify_one();
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_cv_;
+  char *dst_ = nullptr;
+  const char *src_ = nullptr;
+  size_t bytes_ = 0, slice_ = 0;
+  int pending_ = 0;
+  uint64_t generation_ = 0;
+  bool stop_ = false, started_ = false;
+};
+CopyPool g_copy_pool;
+
+struct PinnedStage {   // per stream: pinned twins of the device staging buffers + "results are in the bounce buffer" event
+  void *buf[kPipeSlots] = {};
+  size_t cap[kPipeSlots] = {};
+  cudaEvent_t done = nullptr;
+} g_pin[kPipeStreams];
+
+int pin_reserve(void *&p, size_t &cap, size_t bytes) {
+  if (bytes <= cap) return CUZK_OK;
+  if (p) CK(cudaFreeHost(p));
+  p = nullptr;
+  cap = 0;
+  CK(cudaHostAlloc(&p, bytes, cudaHostAllocDefault));
+  cap = bytes;
+  return CUZK_OK;
+}
+void pin_stop() {
+  for (auto &st : g_pin) {
+    for (int j = 0; j < kPipeSlots; ++j) {
+      if (st.buf[j]) cudaFreeHost(st.buf[j]);
+      st.buf[j] = nullptr;
+      st.cap[j] = 0;
+    }
+    if (st.done) cudaEventDestroy(st.done);
+    st.done = nullptr;
+  }
+}
+bool is_pageable(const void *p) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return attr.type == cudaMemoryTypeUnregistered;
+}
+
+// bulk copies between caller host memory and device memory on stream `st`; pageable memory goes through the pinned
+// bounce buffers in 8 MiB pieces filled / drained by the copy pool.  Both return with the copy complete or enqueued such
+// that `host` may be reused (upload) / read (download) by the caller.  Call with g_hp_mu held.
+constexpr size_t kBulkPiece = (size_t)8 << 20;
+int bulk_upload(void *dev, const void *host, size_t bytes, cudaStream_t st) {
+  if (bytes < ((size_t)4 << 20) || !is_pageable(host)) {
+    CK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, st));
+    return CUZK_OK;
+  }
+  int rc;
+  for (int s = 0; s < kPipeStreams; ++s) {
+    if ((rc = pin_reserve(g_pin[s].buf[0], g_pin[s].cap[0], kBulkPiece))) return rc;
+    if (!g_pin[s].done) CK(cudaEventCreateWithFlags(&g_pin[s].done, cudaEventDisableTiming));
+  }
+  bool used[kPipeStreams] = {};
+  size_t at = 0;
+  for (int c = 0; at < bytes; ++c) {
+    const int s = c % kPipeStreams;
+    const size_t m = std::min(kBulkPiece, bytes - at);
+    if (used[s]) CK(cudaEventSynchronize(g_pin[s].done));   // the piece that used this bounce buffer has left it
+    g_copy_pool.copy(g_pin[s].buf[0], static_cast<const char *>(host) + at, m);
+    CK(cudaMemcpyAsync(static_cast<char *>(dev) + at, g_pin[s].buf[0], m, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(g_pin[s].done, st));
+    used[s] = true;
+    at += m;
+  }
+  for (int s = 0; s < kPipeStreams; ++s)
+    if (used[s]) CK(cudaEventSynchronize(g_pin[s].done));
+  return CUZK_OK;
+}
+int bulk_download(void *host, const void *dev, size_t bytes, cudaStream_t st) {
+  if (bytes < ((size_t)4 << 20) || !is_pageable(host)) {
+    CK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return CUZK_OK;
+  }
+  int rc;
+  for (int s = 0; s < kPipeStreams; ++s) {
+    if ((rc = pin_reserve(g_pin[s].buf[0], g_pin[s].cap[0], kBulkPiece))) return rc;
+    if (!g_pin[s].done) CK(cudaEventCreateWithFlags(&g_pin[s].done, cudaEventDisableTiming));
+  }
+  size_t pending_at[kPipeStreams] = {}, pending_m[kPipeStreams] = {};
+  auto drain = [&](int s) -> int {
+    if (!pending_m[s]) return CUZK_OK;
+    CK(cudaEventSynchronize(g_pin[s].done));
+    g_copy_pool.copy(static_cast<char *>(host) + pending_at[s], g_pin[s].buf[0], pending_m[s]);
+    pending_m[s] = 0;
+    return CUZK_OK;
+  };
+  size_t at = 0;
+  for (int c = 0; at < bytes; ++c) {
+    const int s = c % kPipeStreams;
+    const size_t m = std::min(kBulkPiece, bytes - at);
+    if ((rc = drain(s))) return rc;
+    CK(cudaMemcpyAsync(g_pin[s].buf[0], static_cast<const char *>(dev) + at, m, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(g_pin[s].done, st));
+    pending_at[s] = at;
+    pending_m[s] = m;
+    at += m;
+  }
+  for (int s = 0; s < kPipeStreams; ++s)
+    if ((rc = drain(s))) return rc;
+  return CUZK_OK;
+}
+
 // Chunked, double-buffered host->device->host pass.  `nin` input arrays of `in_bytes[k]` bytes per unit, one output
 // array of `out_bytes` per unit (out may alias in[0] for in-place ops).  launch(stream, d_in[], d_out, m) enqueues the
 // kernel(s) for m units.  Returns after every result byte is in `out`.
@@ -548,25 +727,65 @@ int host_pipeline(size_t n, size_t chunk, int nin, const void *const *in, const 
   int rc = hp_start();
   if (rc) return rc;
   if (chunk > n) chunk = n;
+  size_t unit_bytes = out_bytes;
+  for (int k = 0; k < nin; ++k) unit_bytes += in_bytes[k];
+  // pageable caller memory and enough of it: go through the pinned bounce buffers (bounded to 16 MiB per array and slot)
+  bool staged = n * unit_bytes >= ((size_t)4 << 20) && (is_pageable(out) || is_pageable(in[0]));
+  if (staged) {
+    size_t widest = out_bytes;
+    for (int k = 0; k < nin; ++k) widest = std::max(widest, in_bytes[k]);
+    chunk = std::max<size_t>(1, std::min(chunk, ((size_t)16 << 20) / widest));
+  }
   for (int s = 0; s < kPipeStreams; ++s) {
     for (int k = 0; k < nin; ++k)
       if ((rc = hp_reserve(g_hp.buf[s][k], g_hp.cap[s][k], chunk * in_bytes[k]))) return rc;
     if (!out_aliases_in0 && (rc = hp_reserve(g_hp.buf[s][kPipeSlots - 1], g_hp.cap[s][kPipeSlots - 1], chunk * out_bytes))) return rc;
+    if (staged) {
+      for (int k = 0; k < nin; ++k)
+        if ((rc = pin_reserve(g_pin[s].buf[k], g_pin[s].cap[k], chunk * in_bytes[k]))) return rc;
+      if ((rc = pin_reserve(g_pin[s].buf[kPipeSlots - 1], g_pin[s].cap[kPipeSlots - 1], chunk * out_bytes))) return rc;
+      if (!g_pin[s].done) CK(cudaEventCreateWithFlags(&g_pin[s].done, cudaEventDisableTiming));
+    }
   }
   size_t done = 0;
+  size_t drain_at[kPipeStreams] = {}, drain_m[kPipeStreams] = {};   // staged mode: the chunk whose results sit in each bounce buffer
+  auto drain = [&](int s) -> int {
+    if (drain_m[s] == 0) return CUZK_OK;
+    CK(cudaEventSynchronize(g_pin[s].done));
+    g_copy_pool.copy(static_cast<char *>(out) + drain_at[s] * out_bytes, g_pin[s].buf[kPipeSlots - 1], drain_m[s] * out_bytes);
+    drain_m[s] = 0;
+    return CUZK_OK;
+  };
   for (int c = 0; done < n; ++c) {
     const int s = c % kPipeStreams;
     const size_t m = (n - done < chunk) ? n - done : chunk;
     cudaStream_t st = g_hp.stream[s];
     void *d_in[kPipeSlots] = {};
+    if (staged && (rc = drain(s))) return rc;   // the slot's previous results leave before its buffers are reused
     for (int k = 0; k < nin; ++k) {
       d_in[k] = g_hp.buf[s][k];
-      CK(cudaMemcpyAsync(d_in[k], static_cast<const char *>(in[k]) + done * in_bytes[k], m * in_bytes[k], cudaMemcpyHostToDevice, st));
+      const char *src = static_cast<const char *>(in[k]) + done * in_bytes[k];
+      if (staged) {
+        g_copy_pool.copy(g_pin[s].buf[k], src, m * in_bytes[k]);
+        src = static_cast<const char *>(g_pin[s].buf[k]);
+      }
+      CK(cudaMemcpyAsync(d_in[k], src, m * in_bytes[k], cudaMemcpyHostToDevice, st));
     }
     void *d_out = out_aliases_in0 ? d_in[0] : g_hp.buf[s][kPipeSlots - 1];
     if ((rc = launch(st, d_in, d_out, m))) return rc;
-    CK(cudaMemcpyAsync(static_cast<char *>(out) + done * out_bytes, d_out, m * out_bytes, cudaMemcpyDeviceToHost, st));
+    if (staged) {
+      CK(cudaMemcpyAsync(g_pin[s].buf[kPipeSlots - 1], d_out, m * out_bytes, cudaMemcpyDeviceToHost, st));
+      CK(cudaEventRecord(g_pin[s].done, st));
+      drain_at[s] = done;
+      drain_m[s] = m;
+    } else {
+      CK(cudaMemcpyAsync(static_cast<char *>(out) + done * out_bytes, d_out, m * out_bytes, cudaMemcpyDeviceToHost, st));
+    }
     done += m;
+  }
+  if (staged) {
+    for (int s = 0; s < kPipeStreams; ++s)
+      if ((rc = drain(s))) return rc;
   }
   for (int s = 0; s < kPipeStreams; ++s) CK(cudaStreamSynchronize(g_hp.stream[s]));
   return CUZK_OK;
@@ -890,6 +1109,7 @@ int cuzk_shutdown(void) {
     {
       std::lock_guard<std::mutex> lk2(g_hp_mu);
       hp_stop();
+      pin_stop();
       subtree_streams_stop();
     }
     g_device = -1;
@@ -1060,12 +1280,10 @@ int cuzk_merkle_build(const uint64_t *leaves, size_t n, unsigned arity, uint64_t
   size_t tot = cuzk_merkle_total_nodes(n, arity);
   void *dl, *dv;
   if ((rc = ws_get(0, n * 32, &dl)) || (rc = ws_get(1, tot * 32, &dv))) return rc;
-  CK(cudaMemcpyAsync(dl, leaves, n * 32, cudaMemcpyHostToDevice, st));
+  if ((rc = bulk_upload(dl, leaves, n * 32, st))) return rc;
   rc = merkle_build_dev(static_cast<uint64_t *>(dl), n, arity, static_cast<uint64_t *>(dv), st);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(levels_out, dv, tot * 32, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  return CUZK_OK;
+  return bulk_download(levels_out, dv, tot * 32, st);
 }
 
 int cuzk_merkle_build_batch(const uint64_t *leaves, size_t n, size_t num_trees, unsigned arity, uint64_t *levels_out, int mem,
@@ -1082,12 +1300,10 @@ int cuzk_merkle_build_batch(const uint64_t *leaves, size_t n, size_t num_trees, 
   const size_t tot = cuzk_merkle_total_nodes(n, arity) * num_trees;
   void *dl, *dv;
   if ((rc = ws_get(0, n * num_trees * 32, &dl)) || (rc = ws_get(1, tot * 32, &dv))) return rc;
-  CK(cudaMemcpyAsync(dl, leaves, n * num_trees * 32, cudaMemcpyHostToDevice, st));
+  if ((rc = bulk_upload(dl, leaves, n * num_trees * 32, st))) return rc;
   rc = merkle_build_dev(static_cast<uint64_t *>(dl), n, arity, static_cast<uint64_t *>(dv), st, num_trees);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(levels_out, dv, tot * 32, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  return CUZK_OK;
+  return bulk_download(levels_out, dv, tot * 32, st);
 }
 
 int cuzk_merkle_subtree_roots(const uint64_t *leaves, size_t n, unsigned arity, unsigned height, size_t count,
@@ -1226,9 +1442,8 @@ int cuzk_tree_build(const uint64_t *leaves, size_t n, unsigned arity, int mem, v
   } else {
     std::lock_guard<std::mutex> lk(g_hp_mu);
     void *dl;
-    if (!(rc = ws_get(0, n * 32, &dl))) {
-      e = cudaMemcpyAsync(dl, leaves, n * 32, cudaMemcpyHostToDevice, st);
-      rc = e == cudaSuccess ? merkle_build_dev(static_cast<uint64_t *>(dl), n, arity, t->levels, st) : cuda_fail(e, "cudaMemcpyAsync");
+    if (!(rc = ws_get(0, n * 32, &dl)) && !(rc = bulk_upload(dl, leaves, n * 32, st))) {
+      rc = merkle_build_dev(static_cast<uint64_t *>(dl), n, arity, t->levels, st);
       if (!rc && (e = cudaStreamSynchronize(st)) != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize");
     }
   }
@@ -1271,9 +1486,29 @@ int cuzk_tree_root(const cuzk_tree_t *t, uint64_t *root_out, int mem, void *stre
 int cuzk_tree_levels(const cuzk_tree_t *t, uint64_t *levels_out, int mem, void *stream) {
   if (!t || !levels_out) return fail(CUZK_ERR_INVALID, "null pointer");
   cudaStream_t st = S(stream);
-  CK(cudaMemcpyAsync(levels_out, t->levels, t->total * 32, mem == CUZK_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
-  if (mem != CUZK_MEM_DEVICE) CK(cudaStreamSynchronize(st));
-  return CUZK_OK;
+  if (mem == CUZK_MEM_DEVICE) {
+    CK(cudaMemcpyAsync(levels_out, t->levels, t->total * 32, cudaMemcpyDeviceToDevice, st));
+    return CUZK_OK;
+  }
+  std::lock_guard<std::mutex> lk(g_hp_mu);
+  return bulk_download(levels_out, t->levels, t->total * 32, st);
+}
+
+int cuzk_tree_level(const cuzk_tree_t *t, size_t level, uint64_t *level_out, int mem, void *stream) {
+  if (!t || !level_out) return fail(CUZK_ERR_INVALID, "null pointer");
+  if (level >= t->nlevels) return fail(CUZK_ERR_INVALID, "cuzk_tree_level: no such level");
+  size_t off = 0, width = t->padded;
+  for (size_t l = 0; l < level; ++l) {
+    off += width;
+    width /= t->arity;
+  }
+  cudaStream_t st = S(stream);
+  if (mem == CUZK_MEM_DEVICE) {
+    CK(cudaMemcpyAsync(level_out, t->levels + 4 * off, width * 32, cudaMemcpyDeviceToDevice, st));
+    return CUZK_OK;
+  }
+  std::lock_guard<std::mutex> lk(g_hp_mu);
+  return bulk_download(level_out, t->levels + 4 * off, width * 32, st);
 }
 
 int cuzk_tree_prove_batch(const cuzk_tree_t *t, const uint64_t *indices, size_t num_proofs, uint64_t *siblings_out,

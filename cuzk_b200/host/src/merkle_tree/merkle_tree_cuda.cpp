@@ -49,6 +49,8 @@ CudaNaryMerkleTree::~CudaNaryMerkleTree() = default;
 
 bool CudaNaryMerkleTree::build_tree(const std::vector<FieldElement> &leaves) {
   tree_levels_.clear();
+  device_tree_.reset();
+  levels_on_host_ = true;
   if (leaves.empty()) {  // an empty input clears the tree (merkle_tree_cuda.cu:142-148)
     leaf_count_ = 0;
     tree_height_ = 0;
@@ -58,16 +60,41 @@ bool CudaNaryMerkleTree::build_tree(const std::vector<FieldElement> &leaves) {
   if (!ensure_library()) return false;
   const unsigned arity = (unsigned)config_.arity;
   const size_t n = leaves.size();
-  std::vector<FieldElement> flat(cuzk_merkle_total_nodes(n, arity));
-  if (cuzk_merkle_build(raw(leaves), n, arity, raw(flat), CUZK_MEM_HOST, nullptr) != CUZK_OK) {
+  cuzk_tree_t *handle = nullptr;
+  if (cuzk_tree_build(raw(leaves), n, arity, CUZK_MEM_HOST, nullptr, &handle) != CUZK_OK ||
+      cuzk_tree_root(handle, root_.limbs, CUZK_MEM_HOST, nullptr) != CUZK_OK) {
     std::cerr << "CudaNaryMerkleTree::build_tree: " << cuzk_last_error() << std::endl;
+    if (handle) cuzk_tree_free(handle);
     leaf_count_ = 0;
     tree_height_ = 0;
     leaves_.clear();
     return false;
   }
-  adopt_levels(leaves, flat.data());
+  device_tree_ = std::shared_ptr<void>(handle, [](void *h) { cuzk_tree_free(static_cast<cuzk_tree_t *>(h)); });
+  if (&leaves != &leaves_) leaves_ = leaves;
+  leaf_count_ = n;
+  tree_height_ = cuzk_merkle_tree_height(n, arity);  // the reference's float formula: a getter value only
+  levels_on_host_ = false;
   return true;
+}
+
+// downloads the level arrays the first time they are needed on the host, one copy per level straight into its vector
+void CudaNaryMerkleTree::fetch_levels() const {
+  if (levels_on_host_) return;
+  const cuzk_tree_t *t = static_cast<const cuzk_tree_t *>(device_tree_.get());
+  const size_t nlevels = cuzk_tree_num_levels(t);
+  size_t width = cuzk_merkle_padded_leaves(leaf_count_, (unsigned)config_.arity);
+  tree_levels_.assign(nlevels, {});
+  for (size_t l = 0; l < nlevels; ++l) {
+    tree_levels_[l].resize(width);
+    if (cuzk_tree_level(t, l, raw(tree_levels_[l]), CUZK_MEM_HOST, nullptr) != CUZK_OK) {
+      std::cerr << "CudaNaryMerkleTree: level download failed: " << cuzk_last_error() << std::endl;
+      tree_levels_.clear();
+      return;
+    }
+    width /= config_.arity;
+  }
+  levels_on_host_ = true;
 }
 
 // takes over the flat level-major array the library produced for `leaves` (level 0 = padded leaves, last = root)
@@ -77,6 +104,8 @@ void CudaNaryMerkleTree::adopt_levels(const std::vector<FieldElement> &leaves, c
   leaves_ = leaves;
   leaf_count_ = n;
   tree_height_ = cuzk_merkle_tree_height(n, arity);  // the reference's float formula: a getter value only
+  device_tree_.reset();   // forest builds hand every level over on the host
+  levels_on_host_ = true;
   const size_t nlevels = cuzk_merkle_num_levels(n, arity);
   tree_levels_.clear();
   tree_levels_.reserve(nlevels);
@@ -86,10 +115,13 @@ void CudaNaryMerkleTree::adopt_levels(const std::vector<FieldElement> &leaves, c
     at += width;
     width /= arity;
   }
+  root_ = tree_levels_.back()[0];
 }
 
 std::optional<MerkleProof> CudaNaryMerkleTree::generate_proof(size_t leaf_index) const {
-  if (leaf_index >= leaf_count_ || tree_levels_.empty()) return std::nullopt;
+  if (leaf_index >= leaf_count_ || !has_tree()) return std::nullopt;
+  fetch_levels();
+  if (tree_levels_.empty()) return std::nullopt;
   const size_t arity = config_.arity, nlv = tree_levels_.size() - 1;
   MerkleProof proof;
   proof.leaf_index = leaf_index;
@@ -122,7 +154,7 @@ std::vector<MerkleProof> CudaNaryMerkleTree::generate_batch_proofs(const std::ve
 bool CudaNaryMerkleTree::verify_batch_proofs_each(const std::vector<MerkleProof> &proofs, const std::vector<FieldElement> &leaf_values,
                                                   std::vector<uint8_t> &results) const {
   results.assign(proofs.size(), 0);
-  if (proofs.size() != leaf_values.size() || proofs.empty() || tree_levels_.empty()) return false;
+  if (proofs.size() != leaf_values.size() || proofs.empty() || !has_tree()) return false;
   if (!ensure_library()) return false;
   const size_t arity = config_.arity, sib_per_level = arity - 1;
   const FieldElement root = get_root_hash();
@@ -163,7 +195,7 @@ bool CudaNaryMerkleTree::verify_batch_proofs(const std::vector<MerkleProof> &pro
 }
 
 bool CudaNaryMerkleTree::verify_proof(const MerkleProof &proof, const FieldElement &leaf_value) const {
-  if (tree_levels_.empty()) return false;
+  if (!has_tree()) return false;
   return verify_batch_proofs(std::vector<MerkleProof>{proof}, std::vector<FieldElement>{leaf_value});
 }
 
@@ -202,8 +234,8 @@ bool CudaNaryMerkleTree::build_batch_trees(const std::vector<std::vector<FieldEl
 }
 
 FieldElement CudaNaryMerkleTree::get_root_hash() const {
-  if (tree_levels_.empty() || tree_levels_.back().empty()) return compute_empty_hash(config_.arity);
-  return tree_levels_.back()[0];
+  if (!has_tree()) return compute_empty_hash(config_.arity);  // merkle_tree.cpp:304-309
+  return root_;
 }
 
 FieldElement CudaNaryMerkleTree::compute_empty_hash(size_t arity) const {
@@ -214,6 +246,7 @@ FieldElement CudaNaryMerkleTree::compute_empty_hash(size_t arity) const {
 }
 
 void CudaNaryMerkleTree::print_tree() const {
+  fetch_levels();
   std::cout << "CUDA Merkle Tree (arity=" << config_.arity << ", height=" << tree_height_ << "):" << std::endl;
   for (size_t l = tree_levels_.size(); l-- > 0;) {
     const auto &level = tree_levels_[l];

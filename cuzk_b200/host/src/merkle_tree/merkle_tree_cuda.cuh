@@ -61,7 +61,10 @@ public:
   size_t get_leaf_count() const { return leaf_count_; }
   size_t get_tree_height() const { return tree_height_; }
   const std::vector<FieldElement> &get_leaves() const { return leaves_; }
-  const std::vector<std::vector<FieldElement>> &get_tree_levels() const { return tree_levels_; }
+  const std::vector<std::vector<FieldElement>> &get_tree_levels() const {
+    fetch_levels();
+    return tree_levels_;
+  }
   void print_tree() const;
 
   // root / leaf count / arity equality with the reference's CPU tree.  A template so that this header does not need the
@@ -80,10 +83,18 @@ public:
 private:
   MerkleTreeConfig config_;
   std::vector<FieldElement> leaves_;
-  std::vector<std::vector<FieldElement>> tree_levels_;  // host copy of every level, like the reference class keeps
   size_t leaf_count_;
   size_t tree_height_;
+  // A single-tree build leaves the levels in HBM (a cuzk_tree_t, shared by copies of this object) and fetches only the
+  // root; the host copy the reference class keeps (level 0 = padded leaves ... last = root) is downloaded the first time
+  // a caller asks for levels or proofs.
+  std::shared_ptr<void> device_tree_;
+  FieldElement root_;
+  mutable std::vector<std::vector<FieldElement>> tree_levels_;
+  mutable bool levels_on_host_ = true;
 
+  void fetch_levels() const;
+  bool has_tree() const { return leaf_count_ != 0; }
   FieldElement compute_empty_hash(size_t arity) const;
   void adopt_levels(const std::vector<FieldElement> &leaves, const FieldElement *flat_levels);
 };

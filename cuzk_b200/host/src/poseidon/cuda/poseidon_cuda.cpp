@@ -43,9 +43,13 @@ bool CudaPoseidonHash::batch_hash_single(const std::vector<FieldElement> &inputs
     outputs.clear();
     return true;
   }
-  std::vector<FieldElement> out(inputs.size());
-  if (cuzk_poseidon_hash_single(raw(inputs), raw(out), inputs.size(), CUZK_MEM_HOST, nullptr) != CUZK_OK) return report("batch_hash_single");
-  outputs.swap(out);
+  // written in place: the library uploads a chunk's inputs before it stores that chunk's outputs, so `outputs` may even be
+  // the input vector itself; reusing the caller's capacity avoids a 32 B/hash allocation and page-fault pass per call
+  const size_t n = inputs.size();
+  const uint64_t *in = raw(inputs);
+  outputs.resize(n);
+  if (&outputs == &inputs) in = raw(outputs);
+  if (cuzk_poseidon_hash_single(in, raw(outputs), n, CUZK_MEM_HOST, nullptr) != CUZK_OK) return report("batch_hash_single");
   return true;
 }
 
@@ -63,9 +67,9 @@ bool CudaPoseidonHash::batch_hash_pairs(const std::vector<FieldElement> &left, c
     outputs.clear();
     return true;
   }
-  std::vector<FieldElement> out(left.size());
-  if (cuzk_poseidon_hash_pairs(raw(left), raw(right), raw(out), left.size(), CUZK_MEM_HOST, nullptr) != CUZK_OK) return report("batch_hash_pairs");
-  outputs.swap(out);
+  const size_t n = left.size();
+  outputs.resize(n);  // in place, see batch_hash_single; sizes are equal, so resizing cannot move an aliased input
+  if (cuzk_poseidon_hash_pairs(raw(left), raw(right), raw(outputs), n, CUZK_MEM_HOST, nullptr) != CUZK_OK) return report("batch_hash_pairs");
   return true;
 }
 

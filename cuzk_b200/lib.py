@@ -114,6 +114,7 @@ _SIGS = {
     "cuzk_tree_device_levels": (C.c_void_p, [C.c_void_p]),
     "cuzk_tree_root": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "cuzk_tree_levels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "cuzk_tree_level": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]),
     "cuzk_tree_prove_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "cuzk_tree_verify_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "cuzk_tree_update_leaves": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),

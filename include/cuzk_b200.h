@@ -167,6 +167,8 @@ const uint64_t *cuzk_tree_device_levels(const cuzk_tree_t *tree);
 int cuzk_tree_root(const cuzk_tree_t *tree, uint64_t *root_out, int mem, void *stream);
 /* get_tree_levels (merkle_tree_cuda.cuh:89): copies every level out, level-major */
 int cuzk_tree_levels(const cuzk_tree_t *tree, uint64_t *levels_out, int mem, void *stream);
+/* one level (0 = padded leaves ... num_levels-1 = root), padded_leaves / arity^level elements */
+int cuzk_tree_level(const cuzk_tree_t *tree, size_t level, uint64_t *level_out, int mem, void *stream);
 /* generate_batch_proofs / verify_batch_proofs against the tree's own levels and root; layouts of cuzk_merkle_prove_batch */
 int cuzk_tree_prove_batch(const cuzk_tree_t *tree, const uint64_t *indices, size_t num_proofs, uint64_t *siblings_out,
                           uint32_t *positions_out, int mem, void *stream);

@@ -224,6 +224,15 @@ TEST_F(HostPoseidon, EdgeCasesAndBothClassNames) {
   EXPECT_FALSE(hasher->batch_hash_pairs(three, two, out));
   EXPECT_GT(hasher->get_optimal_batch_size(), 0u);
   EXPECT_GT(hasher->get_max_batch_size(), hasher->get_optimal_batch_size());
+  // outputs may be one of the input vectors (written in place, chunk by chunk)
+  auto a = random_elements(250000, 31, true), b = random_elements(250000, 32, true);
+  std::vector<FieldElement> want_pairs, want_single;
+  ASSERT_TRUE(hasher->batch_hash_pairs(a, b, want_pairs));
+  ASSERT_TRUE(hasher->batch_hash_single(b, want_single));
+  ASSERT_TRUE(hasher->batch_hash_pairs(a, b, a));
+  EXPECT_TRUE(a == want_pairs);
+  ASSERT_TRUE(hasher->batch_hash_single(b, b));
+  EXPECT_TRUE(b == want_single);
   Poseidon::PoseidonCUDAOptimized::CudaPoseidonHashOptimized optimized;
   ASSERT_TRUE(optimized.is_initialized());
   EXPECT_TRUE(verify_cuda_implementations_match(*hasher, optimized, "CUDA Original", "CUDA Optimized", 100));
