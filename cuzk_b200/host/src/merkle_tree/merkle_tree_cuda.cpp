@@ -118,8 +118,41 @@ void CudaNaryMerkleTree::adopt_levels(const std::vector<FieldElement> &leaves, c
   root_ = tree_levels_.back()[0];
 }
 
+// proofs gathered by the GPU from the levels in HBM (cuzk_tree_prove_batch) and unpacked into MerkleProof objects
+bool CudaNaryMerkleTree::proofs_from_device(const std::vector<size_t> &valid_leaves, std::vector<MerkleProof> &out) const {
+  const cuzk_tree_t *t = static_cast<const cuzk_tree_t *>(device_tree_.get());
+  const size_t arity = config_.arity, nlv = cuzk_tree_num_levels(t) - 1, q = valid_leaves.size(), per = arity - 1;
+  std::vector<uint64_t> idx(valid_leaves.begin(), valid_leaves.end());
+  std::vector<FieldElement> sib(q * nlv * per);
+  std::vector<uint32_t> pos(q * nlv);
+  if (nlv && cuzk_tree_prove_batch(t, idx.data(), q, raw(sib), pos.data(), CUZK_MEM_HOST, nullptr) != CUZK_OK) {
+    std::cerr << "CudaNaryMerkleTree: device proof generation failed: " << cuzk_last_error() << std::endl;
+    return false;
+  }
+  out.reserve(out.size() + q);
+  for (size_t k = 0; k < q; ++k) {
+    out.emplace_back();
+    MerkleProof &p = out.back();
+    p.leaf_index = valid_leaves[k];
+    p.path.resize(nlv);
+    p.indices.resize(nlv);
+    for (size_t l = 0; l < nlv; ++l) {
+      const FieldElement *src = sib.data() + (k * nlv + l) * per;
+      p.path[l].assign(src, src + per);
+      p.indices[l] = pos[k * nlv + l];
+    }
+  }
+  device_proofs_served_ += q;
+  return true;
+}
+
 std::optional<MerkleProof> CudaNaryMerkleTree::generate_proof(size_t leaf_index) const {
   if (leaf_index >= leaf_count_ || !has_tree()) return std::nullopt;
+  // a few single proofs are served from the device tree; a caller that keeps asking gets the host copy (one download)
+  if (!levels_on_host_ && device_proofs_served_ < 64) {
+    std::vector<MerkleProof> one;
+    if (proofs_from_device({leaf_index}, one)) return std::move(one[0]);
+  }
   fetch_levels();
   if (tree_levels_.empty()) return std::nullopt;
   const size_t arity = config_.arity, nlv = tree_levels_.size() - 1;
@@ -143,10 +176,23 @@ std::optional<MerkleProof> CudaNaryMerkleTree::generate_proof(size_t leaf_index)
 
 std::vector<MerkleProof> CudaNaryMerkleTree::generate_batch_proofs(const std::vector<size_t> &indices) const {
   std::vector<MerkleProof> proofs;
+  if (!has_tree()) return proofs;
+  if (!levels_on_host_) {
+    // the batch is gathered on the GPU unless it is so large that downloading the tree once is cheaper
+    std::vector<size_t> valid;
+    valid.reserve(indices.size());
+    for (size_t i : indices)
+      if (i < leaf_count_) valid.push_back(i);   // invalid indices are skipped silently, as in the reference
+    const cuzk_tree_t *t = static_cast<const cuzk_tree_t *>(device_tree_.get());
+    const size_t proof_elems = valid.size() * (cuzk_tree_num_levels(t) - 1) * (config_.arity - 1);
+    if (proof_elems < cuzk_tree_total_nodes(t) * 2 && proofs_from_device(valid, proofs)) return proofs;
+    proofs.clear();
+    fetch_levels();
+  }
   proofs.reserve(indices.size());
   for (size_t i : indices) {
     auto p = generate_proof(i);
-    if (p) proofs.push_back(std::move(*p));  // invalid indices are skipped silently, as in the reference
+    if (p) proofs.push_back(std::move(*p));
   }
   return proofs;
 }

@@ -93,7 +93,10 @@ private:
   mutable std::vector<std::vector<FieldElement>> tree_levels_;
   mutable bool levels_on_host_ = true;
 
+  mutable size_t device_proofs_served_ = 0;
+
   void fetch_levels() const;
+  bool proofs_from_device(const std::vector<size_t> &valid_leaves, std::vector<MerkleProof> &out) const;
   bool has_tree() const { return leaf_count_ != 0; }
   FieldElement compute_empty_hash(size_t arity) const;
   void adopt_levels(const std::vector<FieldElement> &leaves, const FieldElement *flat_levels);

@@ -62,7 +62,7 @@ int main(int argc, char **argv) {
   t0 = clk::now();
   const bool ok = tree.verify_batch_proofs(proofs, vals);
   const double verify_ms = ms_since(t0);
-  std::printf("generate_batch_proofs %zu proofs (first call downloads the levels, then host indexing) : %8.3f ms   verify_batch_proofs : %8.3f ms  %8.1f K proofs/s  all valid: %s\n", q,
+  std::printf("generate_batch_proofs %zu proofs (gathered on the GPU from the levels in HBM) : %8.3f ms   verify_batch_proofs : %8.3f ms  %8.1f K proofs/s  all valid: %s\n", q,
               prove_ms, verify_ms, q / verify_ms, ok ? "yes" : "NO");
   std::printf("root %s\n", tree.get_root_hash().to_hex().c_str());
   return ok ? 0 : 4;
