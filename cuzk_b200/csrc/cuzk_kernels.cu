@@ -1375,10 +1375,8 @@ int cuzk_merkle_prove_batch(const uint64_t *levels, size_t n, unsigned arity, co
                                                               static_cast<u64 *>(di), num_proofs, static_cast<uint4 *>(ds),
                                                               static_cast<u32 *>(dp));
   if ((rc = check_launch("merkle_prove_kernel"))) return rc;
-  CK(cudaMemcpyAsync(siblings_out, ds, threads * (arity - 1) * 32, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(positions_out, dp, threads * 4, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  return CUZK_OK;
+  if ((rc = bulk_download(siblings_out, ds, threads * (arity - 1) * 32, st))) return rc;
+  return bulk_download(positions_out, dp, threads * 4, st);
 }
 
 int cuzk_merkle_verify_batch(const uint64_t *leaf_values, const uint64_t *siblings, const uint32_t *positions, size_t levels,
@@ -1531,10 +1529,8 @@ int cuzk_tree_prove_batch(const cuzk_tree_t *t, const uint64_t *indices, size_t 
   if ((rc = ws_get(1, num_proofs * 8, &di)) || (rc = ws_get(2, sib_bytes, &ds)) || (rc = ws_get(3, threads * 4, &dp))) return rc;
   CK(cudaMemcpyAsync(di, indices, num_proofs * 8, cudaMemcpyHostToDevice, st));
   if ((rc = launch(static_cast<u64 *>(di), static_cast<uint4 *>(ds), static_cast<u32 *>(dp)))) return rc;
-  CK(cudaMemcpyAsync(siblings_out, ds, sib_bytes, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(positions_out, dp, threads * 4, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  return CUZK_OK;
+  if ((rc = bulk_download(siblings_out, ds, sib_bytes, st))) return rc;
+  return bulk_download(positions_out, dp, threads * 4, st);
 }
 
 int cuzk_tree_verify_batch(const cuzk_tree_t *t, const uint64_t *leaf_values, const uint64_t *siblings, const uint32_t *positions,

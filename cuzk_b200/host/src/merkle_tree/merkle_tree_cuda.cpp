@@ -197,6 +197,61 @@ std::vector<MerkleProof> CudaNaryMerkleTree::generate_batch_proofs(const std::ve
   return proofs;
 }
 
+bool CudaNaryMerkleTree::generate_flat_proofs(const std::vector<size_t> &leaf_indices, FlatProofBatch &out) const {
+  out = FlatProofBatch();
+  if (!has_tree()) return false;
+  for (size_t i : leaf_indices)
+    if (i >= leaf_count_) return false;
+  out.arity = config_.arity;
+  out.leaf_indices.assign(leaf_indices.begin(), leaf_indices.end());
+  const size_t q = leaf_indices.size();
+  if (device_tree_) {
+    const cuzk_tree_t *t = static_cast<const cuzk_tree_t *>(device_tree_.get());
+    out.levels = cuzk_tree_num_levels(t) - 1;
+    out.positions.resize(q * out.levels);
+    out.siblings.resize(q * out.levels * (out.arity - 1));
+    if (q && out.levels &&
+        cuzk_tree_prove_batch(t, out.leaf_indices.data(), q, raw(out.siblings), out.positions.data(), CUZK_MEM_HOST, nullptr) != CUZK_OK) {
+      std::cerr << "CudaNaryMerkleTree::generate_flat_proofs: " << cuzk_last_error() << std::endl;
+      return false;
+    }
+    return true;
+  }
+  // forest-built trees hold their levels on the host only
+  out.levels = tree_levels_.size() - 1;
+  out.positions.resize(q * out.levels);
+  out.siblings.resize(q * out.levels * (out.arity - 1));
+  for (size_t k = 0; k < q; ++k) {
+    size_t at = leaf_indices[k];
+    for (size_t l = 0; l < out.levels; ++l) {
+      const size_t slot = at % out.arity, first = at - slot;
+      FieldElement *dst = out.siblings.data() + (k * out.levels + l) * (out.arity - 1);
+      for (size_t c = 0; c < out.arity; ++c)
+        if (c != slot) *dst++ = tree_levels_[l][first + c];
+      out.positions[k * out.levels + l] = (uint32_t)slot;
+      at /= out.arity;
+    }
+  }
+  return true;
+}
+
+bool CudaNaryMerkleTree::verify_flat_proofs(const FlatProofBatch &batch, const std::vector<FieldElement> &leaf_values,
+                                            std::vector<uint8_t> &verdicts) const {
+  verdicts.assign(batch.size(), 0);
+  if (!has_tree() || batch.size() != leaf_values.size() || batch.arity != config_.arity ||
+      batch.positions.size() != batch.size() * batch.levels || batch.siblings.size() != batch.positions.size() * (batch.arity - 1))
+    return false;
+  if (batch.size() == 0) return true;
+  if (!ensure_library()) return false;
+  const FieldElement root = get_root_hash();
+  if (cuzk_merkle_verify_batch(raw(leaf_values), raw(batch.siblings), batch.positions.data(), batch.levels, (unsigned)batch.arity, root.limbs,
+                               verdicts.data(), batch.size(), CUZK_MEM_HOST, nullptr) != CUZK_OK) {
+    std::cerr << "CudaNaryMerkleTree::verify_flat_proofs: " << cuzk_last_error() << std::endl;
+    return false;
+  }
+  return true;
+}
+
 bool CudaNaryMerkleTree::verify_batch_proofs_each(const std::vector<MerkleProof> &proofs, const std::vector<FieldElement> &leaf_values,
                                                   std::vector<uint8_t> &results) const {
   results.assign(proofs.size(), 0);

@@ -27,6 +27,18 @@ namespace MerkleTreeCUDA {
 
 using CudaFieldElement = Poseidon::CudaFieldElement;
 
+// extension (no reference counterpart): a whole batch of proofs in the level-uniform wire format of the C ABI -- what a
+// batch verifier wants instead of one heap-allocated vector per proof level.  For proof q and level l (0 = leaf level):
+//   positions[q * levels + l]                               the own slot            (MerkleProof::indices[l])
+//   siblings[(q * levels + l) * (arity - 1) + s]            the s-th other child    (MerkleProof::path[l][s])
+struct FlatProofBatch {
+  size_t arity = 0, levels = 0;
+  std::vector<uint64_t> leaf_indices;
+  std::vector<uint32_t> positions;
+  std::vector<FieldElement> siblings;
+  size_t size() const { return leaf_indices.size(); }
+};
+
 class CudaNaryMerkleTree {
 public:
   // -- construction: the library is brought up on first use; a tree given leaves is built at once
@@ -54,6 +66,10 @@ public:
   // extension: one verdict per proof (1 = valid) instead of their conjunction
   bool verify_batch_proofs_each(const std::vector<MerkleProof> &proofs, const std::vector<FieldElement> &leaf_values,
                                 std::vector<uint8_t> &verdicts) const;
+
+  // extension: flat proof batches, generated and verified on the GPU without per-proof host objects
+  bool generate_flat_proofs(const std::vector<size_t> &leaf_indices, FlatProofBatch &out) const;   // false on an invalid index
+  bool verify_flat_proofs(const FlatProofBatch &batch, const std::vector<FieldElement> &leaf_values, std::vector<uint8_t> &verdicts) const;
 
   // -- getters (get_tree_height: the reference's floating-point formula; levels: 0 = padded leaves ... last = root)
   FieldElement get_root_hash() const;

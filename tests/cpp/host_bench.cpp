@@ -64,6 +64,20 @@ int main(int argc, char **argv) {
   const double verify_ms = ms_since(t0);
   std::printf("generate_batch_proofs %zu proofs (gathered on the GPU from the levels in HBM) : %8.3f ms   verify_batch_proofs : %8.3f ms  %8.1f K proofs/s  all valid: %s\n", q,
               prove_ms, verify_ms, q / verify_ms, ok ? "yes" : "NO");
+  FlatProofBatch flat;
+  t0 = clk::now();
+  const bool got = tree.generate_flat_proofs(idx, flat);
+  const double fprove_ms = ms_since(t0);
+  std::vector<uint8_t> verdicts;
+  tree.verify_flat_proofs(flat, vals, verdicts);
+  t0 = clk::now();
+  const bool fok = got && tree.verify_flat_proofs(flat, vals, verdicts);
+  const double fverify_ms = ms_since(t0);
+  size_t good = 0;
+  for (uint8_t v : verdicts) good += v;
+  std::printf("generate_flat_proofs  %zu proofs : %8.3f ms   verify_flat_proofs : %8.3f ms  %8.1f K proofs/s  valid: %zu\n", q, fprove_ms,
+              fverify_ms, q / fverify_ms, good);
+  if (!fok || good != q) return 5;
   std::printf("root %s\n", tree.get_root_hash().to_hex().c_str());
   return ok ? 0 : 4;
 }

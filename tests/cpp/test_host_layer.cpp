@@ -369,6 +369,26 @@ TEST_F(HostMerkle, ProofsVerifyAndCorruptionIsCaught) {
     EXPECT_FALSE(tree.verify_batch_proofs(bad, vals));
     EXPECT_FALSE(tree.verify_proof(proofs[9], leaves[10]));
     EXPECT_TRUE(tree.verify_proof(proofs[9], leaves[9]));
+    // flat batches carry the same siblings and slots as the MerkleProof objects, and verify the same way
+    FlatProofBatch flat;
+    std::vector<size_t> all(n);
+    for (size_t i = 0; i < n; ++i) all[i] = i;
+    ASSERT_TRUE(tree.generate_flat_proofs(all, flat));
+    ASSERT_EQ(flat.levels, levels.size() - 1);
+    size_t mismatches = 0;
+    for (size_t i = 0; i < n; ++i)
+      for (size_t l = 0; l < flat.levels; ++l) {
+        mismatches += flat.positions[i * flat.levels + l] != proofs[i].indices[l];
+        for (size_t s2 = 0; s2 + 1 < arity; ++s2)
+          mismatches += flat.siblings[(i * flat.levels + l) * (arity - 1) + s2] != proofs[i].path[l][s2];
+      }
+    EXPECT_EQ(mismatches, 0u);
+    std::vector<uint8_t> verdicts;
+    std::vector<FieldElement> tampered = leaves;
+    tampered[5] = FieldElement(tampered[5].limbs[0] + 1);
+    ASSERT_TRUE(tree.verify_flat_proofs(flat, tampered, verdicts));
+    for (size_t i = 0; i < n; ++i) EXPECT_EQ(verdicts[i], i == 5 ? 0 : 1);
+    EXPECT_FALSE(tree.generate_flat_proofs({n}, flat));
   }
 }
 
