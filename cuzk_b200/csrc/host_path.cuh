@@ -267,6 +267,10 @@ int host_pipeline(size_t n, size_t chunk, int nin, const void *const *in, const 
   std::lock_guard<std::mutex> lk(g_hp_mu);
   int rc = hp_start();
   if (rc) return rc;
+  if (const char *env = getenv("CUZK_CHUNK_PERCENT")) {   // tuning knob: chunk size in percent of the default
+    const long pct = atol(env);
+    if (pct > 0) chunk = std::max<size_t>(1, chunk * (size_t)pct / 100);
+  }
   if (chunk > n) chunk = n;
   size_t unit_bytes = out_bytes;
   for (int k = 0; k < nin; ++k) unit_bytes += in_bytes[k];
