@@ -618,3 +618,28 @@ def test_million_pair_hashes_compared_in_full(gpu, oracle):
     bad = np.nonzero((got != want).any(axis=1))[0]
     assert bad.size == 0, (bad[:5], taken)
     assert taken < 1000, f"{taken} of 1e6 hashes took the exact fallback: the fast path should decide almost always"
+
+
+def test_large_host_batches_take_the_staged_path(gpu, oracle):
+    """Host-buffer calls on pageable memory (numpy here, std::vector in the C++ layer) of more than 4 MiB go through the pinned
+    bounce buffers and the copy pool, several chunks deep, in place for the permutation: same results as the device path."""
+    rng = np.random.default_rng(314)
+    n = 700_000                                   # 2 inputs + 1 output of 22 MB each: 2 chunks of the field-op pipeline
+    a, b = rnd(rng, n, False), rnd(rng, n, False)
+    ops = _ops(gpu)
+    for name in ("add", "sub"):
+        got = ops[name](a, b)
+        assert (got == oracle.batch_fr(name, a, b)).all(), name
+    h = gpu.CudaPoseidonHash()
+    m = 45_000                                    # 4.3 MB of states, permuted in place through the staged pipeline
+    st = rnd(rng, 3 * m, False)
+    want = oracle.permutation(st.reshape(-1, 3, 4))
+    got = h.batch_permutation(st.copy())
+    assert (got == want).all()
+    k = 400_000                                   # pair hashes from pageable memory: 4 chunks; spot-check against the oracle
+    l, r = synth_elements(41, k), synth_elements(42, k)
+    out = h.batch_hash_pairs(l, r)
+    sel = np.unique(np.r_[0, k - 1, 113_663, 113_664, 227_327, 227_328, rng.integers(0, k, 500)])
+    assert (out[sel] == oracle.hash_pairs(l[sel], r[sel])).all()
+    dev = to_host(h.batch_hash_pairs(to_dev(l), to_dev(r)))
+    assert (out == dev).all()
