@@ -474,7 +474,9 @@ def ncu_traffic():
     `ncu --set full` capture (profiles/hash_pairs_traffic.json, written by tools/ncu_summary.py); None when absent."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "hash_pairs_traffic.json")))
-        return {"bytes_per_launch": t["dram_bytes_read"] + t["dram_bytes_write"], "source": t["source"]}
+        return {"bytes_per_launch": t["dram_bytes_read"] + t["dram_bytes_write"], "source": t["source"],
+                "ncu_pipe_busy_pct": {"fmaheavy (IMAD.WIDE)": t.get("fmaheavy_pct_of_peak"), "alu": t.get("alu_pct"), "fp64": t.get("fp64_pct")},
+                "ncu_inst_per_hash": t.get("inst_per_hash"), "ncu_imad_wide_per_hash": t.get("imad_wide_per_hash")}
     except Exception:
         return None
 

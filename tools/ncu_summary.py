@@ -49,5 +49,7 @@ if len(sys.argv) > 3:  # also write the per-launch DRAM traffic bench.py reports
     import json
 
     json.dump({"dram_bytes_read": _num("dram__bytes_read.sum"), "dram_bytes_write": _num("dram__bytes_write.sum"),
-               "source": out}, open(sys.argv[3], "w"))
+               "fmaheavy_pct_of_peak": _num("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"),
+               "alu_pct": _num("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"),
+               "source": out}, open(sys.argv[3], "w"), indent=1)
 print(open(out).read())
