@@ -10,7 +10,7 @@
 // size mismatch; get_tree_height() returns the reference's floating-point formula.
 // Deliberate differences: the level arrays are sized by the integer padding loop, never by the float height (the
 // reference builds a spurious extra level at exact powers); the whole tree is built in one
-// host call (one upload, one download) instead of a PCIe round trip per level; batches of every size are verified
+// host call (one upload; the levels stay in HBM until a caller asks for them) instead of a PCIe round trip per level; batches of every size are verified
 // on the GPU (the reference verifies fewer than 32 proofs on the CPU, merkle_tree_cuda.cu:348-355).
 #pragma once
 
@@ -50,7 +50,7 @@ public:
   CudaNaryMerkleTree(const CudaNaryMerkleTree &) = default;
   CudaNaryMerkleTree &operator=(const CudaNaryMerkleTree &) = default;
 
-  // -- GPU build: one upload, every level hashed on the device, one download.  An empty vector clears the tree (true).
+  // -- GPU build: one upload, every level hashed on the device, the root comes back.  An empty vector clears the tree (true).
   bool build_tree(const std::vector<FieldElement> &leaf_values);
   // equal-sized trees are built as one forest pass (cuzk_merkle_build_batch); ragged batches fall back to one build per tree
   static bool build_batch_trees(const std::vector<std::vector<FieldElement>> &leaf_sets, std::vector<CudaNaryMerkleTree> &out_trees,
