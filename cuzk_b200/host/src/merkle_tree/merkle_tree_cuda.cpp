@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstring>
 #include <iostream>
 #include <map>
 #include <mutex>
@@ -267,19 +268,23 @@ bool CudaNaryMerkleTree::verify_batch_proofs_each(const std::vector<MerkleProof>
     if (proofs[q].path.size() == proofs[q].indices.size()) by_len[proofs[q].path.size()].push_back(q);
   for (const auto &group : by_len) {
     const size_t L = group.first, m = group.second.size();
-    std::vector<FieldElement> leaves(m), sib(m * L * sib_per_level, filler);
-    std::vector<uint32_t> pos(m * L);
+    // flat, level-uniform copies of the batch (the layout of cuzk_merkle_verify_batch); raw buffers: every slot is written
+    // exactly once below, so there is nothing to gain from value-initialising ~100 bytes per proof level first
+    std::unique_ptr<uint64_t[]> leaves(new uint64_t[m * 4]), sib(new uint64_t[std::max<size_t>(1, m * L * sib_per_level * 4)]);
+    std::unique_ptr<uint32_t[]> pos(new uint32_t[std::max<size_t>(1, m * L)]);
     for (size_t k = 0; k < m; ++k) {
       const MerkleProof &p = proofs[group.second[k]];
-      leaves[k] = leaf_values[group.second[k]];
+      std::memcpy(leaves.get() + 4 * k, leaf_values[group.second[k]].limbs, 32);
       for (size_t l = 0; l < L; ++l) {
         pos[k * L + l] = p.indices[l] < arity ? (uint32_t)p.indices[l] : 0xFFFFFFFFu;
         const size_t have = std::min(p.path[l].size(), sib_per_level);
-        std::copy(p.path[l].begin(), p.path[l].begin() + have, sib.begin() + (k * L + l) * sib_per_level);
+        uint64_t *dst = sib.get() + (k * L + l) * sib_per_level * 4;
+        if (have) std::memcpy(dst, p.path[l].data(), have * 32);
+        for (size_t s2 = have; s2 < sib_per_level; ++s2) std::memcpy(dst + 4 * s2, filler.limbs, 32);
       }
     }
     std::vector<uint8_t> res(m);
-    if (cuzk_merkle_verify_batch(raw(leaves), raw(sib), pos.data(), L, (unsigned)arity, root.limbs, res.data(), m, CUZK_MEM_HOST, nullptr) !=
+    if (cuzk_merkle_verify_batch(leaves.get(), sib.get(), pos.get(), L, (unsigned)arity, root.limbs, res.data(), m, CUZK_MEM_HOST, nullptr) !=
         CUZK_OK) {
       std::cerr << "CudaNaryMerkleTree::verify_batch_proofs: " << cuzk_last_error() << std::endl;
       return false;
