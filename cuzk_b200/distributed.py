@@ -129,3 +129,18 @@ def sharded_merkle_root(local_leaves, plan: ShardPlan, rank: int, ops, group=Non
 def shard_slice(n: int, rank: int, world: int) -> tuple[int, int]:
     """Contiguous slice of n independent units (hashes, proofs) for `rank`."""
     return n * rank // world, n * (rank + 1) // world
+
+
+def sharded_all_valid(local_results, group=None) -> bool:
+    """AND of per-proof verdicts that were computed shard by shard (``shard_slice`` of the proof batch per rank): one
+    all-reduce(MIN) of a single byte; an empty global batch is False, like CudaNaryMerkleTree::verify_batch_proofs
+    (merkle_tree_cuda.cu:343).  ``local_results`` is this rank's uint8 verdict tensor (may be empty)."""
+    t = local_results
+    if not isinstance(t, torch.Tensor):
+        t = torch.from_numpy(np.ascontiguousarray(t, dtype=np.uint8))
+    flags = torch.stack([(t.min() if t.numel() else torch.ones((), dtype=torch.uint8, device=t.device)).to(torch.int32),
+                         torch.tensor(-int(t.numel() > 0), dtype=torch.int32, device=t.device)])
+    # flags[0]: all of mine valid (1) or not (0) -> MIN;  flags[1]: -(I had proofs) -> MIN is -1 when any rank had some
+    if dist is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN, group=group)
+    return bool(flags[0].item() == 1 and flags[1].item() == -1)

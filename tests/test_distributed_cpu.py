@@ -125,3 +125,36 @@ def test_sharded_root_equals_single_tree_gloo(world, n, arity):
         assert p.exitcode == 0
     for rank, root in got:
         assert root == want, (rank, world, n, arity)
+
+
+def _verify_worker(rank, world, port, nproofs, bad_at, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cuzk_b200.distributed import shard_slice, sharded_all_valid
+
+        lo, hi = shard_slice(nproofs, rank, world)
+        verdicts = np.ones(hi - lo, dtype=np.uint8)          # stands in for this rank's merkle_verify_kernel results
+        if bad_at is not None and lo <= bad_at < hi:
+            verdicts[bad_at - lo] = 0
+        q.put((rank, sharded_all_valid(verdicts)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nproofs,bad_at,want", [(100, None, True), (100, 73, False), (1, None, True), (0, None, False), (3, 0, False)])
+def test_sharded_verify_and_reduce_gloo(nproofs, bad_at, want):
+    """batch verification shards the proofs; the global answer is the AND over ranks (False for an empty batch)."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_verify_worker, args=(r, world, port, nproofs, bad_at, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [g for _, g in got] == [want] * world
