@@ -39,6 +39,7 @@ template <int OP>
 __global__ void __launch_bounds__(kBlock) fr_batch_kernel(const uint4 *__restrict__ a, const uint4 *__restrict__ b,
                                                            uint4 *__restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  fr_table_init();
   if (i >= n) return;
   if (OP == CUZK_FR_SUB) {
     const u64 *pa = reinterpret_cast<const u64 *>(a + 2 * i);
@@ -68,6 +69,7 @@ __global__ void __launch_bounds__(kBlock) fr_batch_kernel(const uint4 *__restric
 // batch_hash_single: state [1, in, 0]
 __global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) hash_single_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  fr_table_init();
   if (i >= n) return;
   u32 r[8];
   sponge_n(r, 1u, 1, [&](u32(&x)[8], int) { load_fr(x, in + 2 * i); });
@@ -78,6 +80,7 @@ __global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) hash_single_kernel(co
 __global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) hash_pairs_kernel(const uint4 *__restrict__ l, const uint4 *__restrict__ r,
                                                              uint4 *__restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  fr_table_init();
   if (i >= n) return;
   u32 h[8];
   sponge_n(h, 2u, 2, [&](u32(&x)[8], int j) { load_fr(x, (j == 0 ? l : r) + 2 * i); });
@@ -87,6 +90,7 @@ __global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) hash_pairs_kernel(con
 // batch_permutation: in-place, caller-supplied (possibly non-canonical) states
 __global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) permutation_kernel(uint4 *states, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  fr_table_init();
   if (i >= n) return;
   u32 s0[8], s1[8], s2[8], unc = 0;
   load_fr_plain(s0, states + 6 * i);
@@ -111,6 +115,7 @@ __global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) permutation_kernel(ui
 // test hook: one MDS layer on canonical states (mode 0 = production fast path with fallback, 1 = exact path only)
 __global__ void __launch_bounds__(kBlock) debug_mds_kernel(uint4 *states, size_t n, int mode) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  fr_table_init();
   if (i >= n) return;
   u32 s0[8], s1[8], s2[8];
   load_fr_plain(s0, states + 6 * i);
@@ -129,6 +134,7 @@ __global__ void __launch_bounds__(kBlock) debug_mds_kernel(uint4 *states, size_t
 __global__ void __launch_bounds__(kBlock) debug_fast_ops_kernel(int op, const uint4 *__restrict__ a, const uint4 *__restrict__ b,
                                                                  uint4 *__restrict__ out, u32 *__restrict__ flags, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  fr_table_init();
   if (i >= n) return;
   u32 x[8], y[8], r[8], unc = 0;
   load_fr(x, a + 2 * i);
@@ -152,6 +158,7 @@ __global__ void __launch_bounds__(kBlock) debug_fast_ops_kernel(int op, const ui
 __global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) sponge_kernel(const uint4 *__restrict__ in, int width, u32 ds_lo, u32 ds_hi,
                                                          uint4 *__restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  fr_table_init();
   if (i >= n) return;
   const uint4 *base = in + 2 * i * (size_t)width;
   u32 r[8];
@@ -162,6 +169,7 @@ __global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) sponge_kernel(const u
 // padding chain for one arity: pad[0] = hash_multiple(arity zeros), pad[l+1] = hash_multiple(arity x pad[l])
 // computes levels [start, end); level start-1 must already be in pad[] when start > 0
 __global__ void padding_chain_kernel(uint4 *pad, int arity, int start, int end) {
+  fr_table_init();
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   u32 cur[8];
   if (start > 0) load_fr_plain(cur, pad + 2 * (start - 1));
@@ -202,6 +210,7 @@ __global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) merkle_level_kernel(c
                                                                size_t ntrees, size_t tree_stride) {
   // forest form: `ntrees` trees of identical shape, tree t at in/out + t * tree_stride elements; thread = (tree, node)
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  fr_table_init();
   if (t >= out_count * ntrees) return;
   const size_t tree = t / out_count, i = t - tree * out_count;
   in += 2 * tree * tree_stride;
@@ -229,6 +238,7 @@ __global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) merkle_fused2_kernel(
                                                                 size_t tree_stride) {
   extern __shared__ uint4 smem[];                    // [2 * arity][kBlock] uint4: slot-major, so a warp's accesses never conflict
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  fr_table_init();
   if (t >= out_count * ntrees) return;
   const size_t tree = t / out_count, i = t - tree * out_count;   // forest form, see merkle_level_kernel
   in += 2 * tree * tree_stride;
@@ -284,6 +294,7 @@ __global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) merkle_fused2_kernel(
 __global__ void merkle_write_leaves_kernel(uint4 *__restrict__ level0, const u64 *__restrict__ indices, const uint4 *__restrict__ values,
                                            size_t count) {
   size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  fr_table_init();
   if (q >= count) return;
   const u64 idx = indices[q];
   level0[2 * idx] = values[2 * q];
@@ -295,6 +306,7 @@ __global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) merkle_update_level_k
                                                                       const u64 *__restrict__ indices, size_t count, u64 divisor,
                                                                       int arity) {
   size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  fr_table_init();
   if (q >= count) return;
   const size_t node = indices[q] / divisor;          // ancestor index at the output level (divisor = arity^l)
   const uint4 *kids = in + 2 * node * (size_t)arity;
@@ -342,6 +354,7 @@ __global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) merkle_verify_kernel(
                                                                 uint8_t *__restrict__ results, size_t num_proofs) {
   // the expected root comes from device memory (`root`) or, for host-buffer calls, by value (root == nullptr)
   size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  fr_table_init();
   if (q >= num_proofs) return;
   u32 cur[8];
   load_fr(cur, leaves + 2 * q);
@@ -389,6 +402,7 @@ __device__ __forceinline__ u64 splitmix64_dev(u64 seed, u64 idx) {
 }
 __global__ void synth_elements_kernel(u64 *out, size_t n, u64 seed, u64 start, int canonical) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  fr_table_init();
   if (i >= n) return;
   u64 v[4];
 #pragma unroll
@@ -398,6 +412,7 @@ __global__ void synth_elements_kernel(u64 *out, size_t n, u64 seed, u64 start, i
 }
 __global__ void synth_u64_leaves_kernel(u64 *out, size_t n, u64 seed, u64 start) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  fr_table_init();
   if (i >= n) return;
   reinterpret_cast<ulonglong4 *>(out)[i] = make_ulonglong4(splitmix64_dev(seed, start + i), 0, 0, 0);
 }
