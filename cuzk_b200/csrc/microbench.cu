@@ -97,6 +97,22 @@ __global__ void __launch_bounds__(256) imad_peak_kernel(u32 *sink, int iters, u3
             hi[4 * c + j] = madc_hi_cc(m, 0x9f60cd29u + 2u * j, hi[4 * c + j]);
           }
         }
+      } else if (VARIANT == 13 || VARIANT == 15) {  // 8 wide mads + 8 (13) or 16 (15) independent DFMAs: do the FP64 and multiplier pipes overlap?
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mad_wide(lo[i], hi[i], lo[i], b);
+        double *d = reinterpret_cast<double *>(lo + 8);   // 4 doubles over lo[8..15]
+        double *d2 = reinterpret_cast<double *>(hi + 8);  // 4 doubles over hi[8..15]
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { d[i] = fma(d[i], 1.0000001, 0.5); d2[i] = fma(d2[i], 0.9999999, 0.25); }
+        if (VARIANT == 15) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { d[i] = fma(d[i], 0.9999999, 0.125); d2[i] = fma(d2[i], 1.0000001, 0.75); }
+        }
+      } else if (VARIANT == 14) {  // 8 wide mads + 8 low IMADs (the form ptxas uses for moves and carry captures)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mad_wide(lo[i], hi[i], lo[i], b);
+#pragma unroll
+        for (int i = 8; i < 16; ++i) lo[i] = lo[i] * b + hi[i];
       } else if (VARIANT == 9) {   // DFMA (FP64 pipe), 8 lanes
         double *d = reinterpret_cast<double *>(lo);  // 8 doubles over lo[16]
 #pragma unroll
@@ -144,6 +160,9 @@ extern "C" int cuzk_imad_peak(int variant, int iters, double *ops_per_second_out
       case 10: imad_peak_kernel<10><<<blocks, threads>>>(sink, iters, 1u + rep); break;
       case 11: imad_peak_kernel<11><<<blocks, threads>>>(sink, iters, 1u + rep); break;
       case 12: imad_peak_kernel<12><<<blocks, threads>>>(sink, iters, 1u + rep); break;
+      case 13: imad_peak_kernel<13><<<blocks, threads>>>(sink, iters, 1u + rep); break;
+      case 14: imad_peak_kernel<14><<<blocks, threads>>>(sink, iters, 1u + rep); break;
+      case 15: imad_peak_kernel<15><<<blocks, threads>>>(sink, iters, 1u + rep); break;
       default: cudaFree(sink); return CUZK_ERR_INVALID;
     }
     cudaEventRecord(e1);
@@ -156,7 +175,7 @@ extern "C" int cuzk_imad_peak(int variant, int iters, double *ops_per_second_out
   cudaEventDestroy(e1);
   cudaFree(sink);
   // counted operations per thread per trip (4 reps): variants 0-4, 8: 64; 5-7: 32 multiply-adds; 9: 64 DFMA
-  double per_trip = (variant >= 5 && variant <= 7) ? 32.0 : 64.0;
+  double per_trip = ((variant >= 5 && variant <= 7) || (variant >= 13 && variant <= 15)) ? 32.0 : 64.0;
   *ops_per_second_out = per_trip * (double)iters * (double)blocks * (double)threads / (best * 1e-3);
   return CUZK_OK;
 }

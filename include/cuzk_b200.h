@@ -208,7 +208,8 @@ int cuzk_debug_fast_ops(int op, const uint64_t *a, const uint64_t *b, uint64_t *
  * chip and returns measured 32x32->64 multiply-adds per second (the roofline denominator); variant selects
  * 0 = IMAD.WIDE.U32, 1 = IMAD (lo), 2 = IMAD.HI, 3 = IMAD.WIDE.U32.X carry chains, 4 = IADD3.X carry chains,
  * 5/6/7 = IMAD.WIDE with 1/2/3 carry-chain adds per multiply (counts the multiplies), 8 = SEL, 9 = DFMA,
- * 10 = IMAD.WIDE.U32 with an immediate multiplier, 11 = multiplier in the constant bank, 12 = immediate-form carry chains */
+ * 10 = IMAD.WIDE.U32 with an immediate multiplier, 11 = multiplier in the constant bank, 12 = immediate-form carry chains,
+ * 13 / 15 = IMAD.WIDE with 1 / 2 independent DFMA per multiply, 14 = IMAD.WIDE with 1 low IMAD per multiply (multiplies counted) */
 int cuzk_imad_peak(int variant, int iters, double *ops_per_second_out);
 
 #ifdef __cplusplus
