@@ -485,3 +485,12 @@ class DeviceMerkleTree:
         idx = indices.to(torch.int64).contiguous() if dev else np.ascontiguousarray(indices, dtype=np.uint64)
         lib.check(lib.cuzk_tree_update_leaves(self._h, _ptr(idx), _ptr(v), v.shape[0], MEM_DEVICE if dev else MEM_HOST, _stream(v)),
                   "cuzk_tree_update_leaves")
+
+    def append_leaves(self, values) -> None:
+        """NaryMerkleTree::insert_leaf for a batch: the tree afterwards equals a fresh build over all leaves"""
+        lib = get_lib()
+        v = _elems(values)
+        lib.check(lib.cuzk_tree_append_leaves(self._h, _ptr(v), v.shape[0], _mem(v), _stream(v)), "cuzk_tree_append_leaves")
+        self.leaf_count = lib.cuzk_tree_leaf_count(self._h)
+        self.num_levels = lib.cuzk_tree_num_levels(self._h)
+        self.total_nodes = lib.cuzk_tree_total_nodes(self._h)

@@ -649,6 +649,70 @@ int cuzk_tree_update_leaves(cuzk_tree_t *t, const uint64_t *indices, const uint6
   return CUZK_OK;
 }
 
+// leaf indices n .. n+count-1 for the append path
+__global__ void iota_u64_kernel(u64 *out, u64 first, size_t count) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = first + i;
+}
+
+int cuzk_tree_append_leaves(cuzk_tree_t *t, const uint64_t *values, size_t count, int mem, void *stream) {
+  int rc = require_init();
+  if (rc) return rc;
+  if (!t) return fail(CUZK_ERR_INVALID, "null tree");
+  if (count == 0) return CUZK_OK;
+  if (!values) return fail(CUZK_ERR_INVALID, "null pointer");
+  cudaStream_t st = S(stream);
+  // bring the new values to the device
+  void *dv = nullptr;
+  cudaError_t e = cudaMallocAsync(&dv, count * 32, st);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(append values)");
+  e = cudaMemcpyAsync(dv, values, count * 32, mem == CUZK_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) { cudaFreeAsync(dv, st); return cuda_fail(e, "cudaMemcpyAsync(append values)"); }
+  if (t->n + count <= t->padded) {
+    // the padded shape does not change: the new leaves replace padding slots and only their ancestors are re-hashed
+    void *di = nullptr;
+    if ((e = cudaMallocAsync(&di, count * 8, st)) != cudaSuccess) { cudaFreeAsync(dv, st); return cuda_fail(e, "cudaMallocAsync(indices)"); }
+    iota_u64_kernel<<<grid_for(count, 256), 256, 0, st>>>(static_cast<u64 *>(di), t->n, count);
+    rc = check_launch("iota_u64_kernel");
+    const size_t old_n = t->n;
+    t->n += count;   // update_leaves checks indices against the new count
+    if (!rc) rc = cuzk_tree_update_leaves(t, static_cast<const uint64_t *>(di), static_cast<const uint64_t *>(dv), count, CUZK_MEM_DEVICE, stream);
+    if (rc) t->n = old_n;
+    cudaFreeAsync(di, st);
+    cudaFreeAsync(dv, st);
+    if (!rc && mem != CUZK_MEM_DEVICE) CK(cudaStreamSynchronize(st));
+    return rc;
+  }
+  // the tree outgrows its padded leaf level: build the larger tree from the old leaves (still in level 0) plus the new ones
+  const size_t n2 = t->n + count;
+  void *all = nullptr;
+  if ((e = cudaMallocAsync(&all, n2 * 32, st)) != cudaSuccess) { cudaFreeAsync(dv, st); return cuda_fail(e, "cudaMallocAsync(leaves)"); }
+  cudaMemcpyAsync(all, t->levels, t->n * 32, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(static_cast<char *>(all) + t->n * 32, dv, count * 32, cudaMemcpyDeviceToDevice, st);
+  const size_t total2 = cuzk_merkle_total_nodes(n2, t->arity);
+  uint64_t *levels2 = nullptr;
+  if ((e = cudaMalloc(&levels2, total2 * 32)) != cudaSuccess) {
+    cudaFreeAsync(all, st);
+    cudaFreeAsync(dv, st);
+    return cuda_fail(e, "cudaMalloc(tree levels)");
+  }
+  rc = merkle_build_dev(static_cast<const uint64_t *>(all), n2, t->arity, levels2, st);
+  cudaFreeAsync(all, st);
+  cudaFreeAsync(dv, st);
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess && !rc) rc = cuda_fail(e, "cudaStreamSynchronize");
+  if (rc) {
+    cudaFree(levels2);
+    return rc;
+  }
+  cudaFree(t->levels);
+  t->levels = levels2;
+  t->n = n2;
+  t->padded = cuzk_merkle_padded_leaves(n2, t->arity);
+  t->total = total2;
+  t->nlevels = cuzk_merkle_num_levels(n2, t->arity);
+  return CUZK_OK;
+}
+
 int cuzk_synth_elements(uint64_t *out, size_t n, uint64_t seed, uint64_t start, int canonical, void *stream) {
   if (n == 0) return CUZK_OK;
   synth_elements_kernel<<<grid_for(n, 256), 256, 0, S(stream)>>>(out, n, seed, start, canonical);

@@ -180,6 +180,12 @@ int cuzk_tree_verify_batch(const cuzk_tree_t *tree, const uint64_t *leaf_values,
 int cuzk_tree_update_leaves(cuzk_tree_t *tree, const uint64_t *indices, const uint64_t *values, size_t count, int mem,
                             void *stream);
 
+/* NaryMerkleTree::insert_leaf (merkle_tree.cpp:290-293; a full rebuild per leaf in the reference) for a batch: appends
+ * values[0..count) after the last leaf.  While the padded leaf level has room only the new leaves' ancestors are re-hashed;
+ * when it overflows, the larger tree is rebuilt on the device from the leaves already there.  Either way the tree equals a
+ * fresh build over all leaves. */
+int cuzk_tree_append_leaves(cuzk_tree_t *tree, const uint64_t *values, size_t count, int mem, void *stream);
+
 /* ---- synthetic inputs: generated on the device so multi-GiB leaf sets need no upload.
  * element i, limb j = splitmix64(seed, 4*(start+i)+j), top limb masked to 60 bits when canonical != 0;
  * u64 leaves: limb 0 = splitmix64(seed, start+i), other limbs 0.  Device pointers only. ---- */

@@ -643,3 +643,27 @@ def test_large_host_batches_take_the_staged_path(gpu, oracle):
     assert (out[sel] == oracle.hash_pairs(l[sel], r[sel])).all()
     dev = to_host(h.batch_hash_pairs(to_dev(l), to_dev(r)))
     assert (out == dev).all()
+
+
+@pytest.mark.parametrize("arity", [2, 3, 8])
+def test_device_tree_append_equals_fresh_build(gpu, oracle, arity):
+    """cuzk_tree_append_leaves (NaryMerkleTree::insert_leaf, batched): appending within the padded level (path re-hash),
+    exactly filling it, and overflowing it (device rebuild) all give the oracle's tree over the concatenated leaves."""
+    rng = np.random.default_rng(200 + arity)
+    leaves = rnd(rng, arity**3 - 5, True)
+    for dev in (False, True):
+        t = gpu.DeviceMerkleTree(to_dev(leaves) if dev else leaves, arity=arity)
+        cur = leaves
+        for extra in (1, 3, 1, arity**3, 7):          # within, up to the brim, over it (twice), within the larger tree
+            add = rnd(rng, extra, extra % 2 == 0)
+            t.append_leaves(to_dev(add) if dev else add)
+            cur = np.concatenate([cur, add])
+            want = oracle.merkle_build(cur, arity)
+            got = t.get_tree_levels()
+            assert t.leaf_count == cur.shape[0]
+            assert len(got) == len(want) and all((g == w).all() for g, w in zip(got, want)), (arity, dev, extra)
+        idx = np.array([0, cur.shape[0] - 1], dtype=np.uint64)
+        pb = t.generate_batch_proofs(to_dev(idx.astype(np.int64)) if dev else idx)
+        res = t.verify_batch_proofs(pb, to_dev(cur[idx.astype(np.int64)]) if dev else cur[idx.astype(np.int64)])
+        assert bool((res.cpu().numpy() if dev else res).all())
+        t.close()
