@@ -62,4 +62,7 @@ build_test test_merkle_tree           "$S/merkle_tree/test/test_merkle_tree.cpp"
 nomain=$(echo $objs | tr ' ' '\n' | grep -v gtest_main | tr '\n' ' ')
 $CXX $FLAGS -DCUDA_ENABLED -I"${CUDA_HOME:-/usr/local/cuda}/include" "$S/poseidon/test/benchmark.cpp" $nomain $LINK -o "$OUT/poseidon_benchmark"
 echo "built oracle/_ref/bin/poseidon_benchmark  <-  src/poseidon/test/benchmark.cpp"
+# the reference's profiling driver (a loop over batch sizes for an external profiler; its own main)
+$CXX $FLAGS "$S/poseidon/cuda/poseidon_cuda_profiler.cpp" $nomain $LINK -o "$OUT/poseidon_cuda_profiler"
+echo "built oracle/_ref/bin/poseidon_cuda_profiler  <-  src/poseidon/cuda/poseidon_cuda_profiler.cpp"
 rm -rf "$FARM"
