@@ -5,6 +5,7 @@
 #include <gtest/gtest.h>
 
 #include <random>
+#include <thread>
 #include <vector>
 
 #include "../../cuzk_b200/host/src/merkle_tree/merkle_tree_cuda.cuh"
@@ -259,6 +260,37 @@ TEST(HostLifecycle, DroppingOneUserKeepsTheOthersAlive) {
   CudaFieldArithmetic::cleanup();  // extra cleanup is harmless
   CudaPoseidonHash c;              // and the library comes back up
   EXPECT_TRUE(c.is_initialized());
+}
+
+TEST(HostLifecycle, ConcurrentCallersGetTheirOwnResults) {
+  // the reference is single-threaded; here host-buffer calls serialise inside the library and must not mix up buffers
+  CudaPoseidonHash shared;
+  ASSERT_TRUE(shared.is_initialized());
+  const int nthreads = 4;
+  std::vector<std::vector<FieldElement>> in(nthreads), want(nthreads);
+  for (int t = 0; t < nthreads; ++t) {
+    in[t] = random_elements(40000 + 1000 * t, 900 + t, true);
+    want[t].resize(in[t].size());
+    for (size_t i = 0; i < in[t].size(); i += 97) cuzk_oracle_hash_single(in[t][i].limbs, want[t][i].limbs);
+  }
+  std::vector<int> bad(nthreads, 0);
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nthreads; ++t)
+    pool.emplace_back([&, t] {
+      CudaPoseidonHash mine;   // a second reference on the library, taken and dropped concurrently
+      for (int rep = 0; rep < 5; ++rep) {
+        std::vector<FieldElement> out;
+        IPoseidonCudaHash &h = (rep & 1) ? static_cast<IPoseidonCudaHash &>(mine) : static_cast<IPoseidonCudaHash &>(shared);
+        if (!h.batch_hash_single(in[t], out) || out.size() != in[t].size()) { bad[t] += 1000; continue; }
+        for (size_t i = 0; i < out.size(); i += 97) bad[t] += out[i] != want[t][i];
+        std::vector<FieldElement> leaves(in[t].begin(), in[t].begin() + 500);
+        CudaNaryMerkleTree tree(leaves, MerkleTreeConfig(2 + t));
+        auto p = tree.generate_proof(17);
+        bad[t] += !(p && tree.verify_proof(*p, leaves[17]));
+      }
+    });
+  for (auto &th : pool) th.join();
+  for (int t = 0; t < nthreads; ++t) EXPECT_EQ(bad[t], 0) << "thread " << t;
 }
 
 // ------------------------------------------------------------------------------------------ Merkle tree
