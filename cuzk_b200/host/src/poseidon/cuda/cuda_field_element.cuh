@@ -49,6 +49,9 @@ struct alignas(32) CudaFieldElement {
   std::string to_hex() const { return static_cast<FieldElement>(*this).to_hex(); }
   std::string to_dec() const { return static_cast<FieldElement>(*this).to_dec(); }
   static CudaFieldElement from_hex(const std::string &hex) { return CudaFieldElement(FieldElement::from_hex(hex)); }
+  // uses the CPU library's FieldElement::random(); a template so that it is only looked up where a caller asks for it
+  template <class FE = FieldElement>
+  static CudaFieldElement random() { return CudaFieldElement(FE::random()); }
 #endif
 };
 
