@@ -356,6 +356,28 @@ def main():
             torch.cuda.synchronize(dev)
             return a0.elapsed_time(a1) / reps, leaves, levels
 
+        def time_build_e2e(leaves, arity, reps):
+            """end to end through the device-resident tree handle: leaves start in pinned HOST memory, the root comes back to the
+            host (cuzk_tree_build + cuzk_tree_root + cuzk_tree_free per step), wall clock"""
+            host = leaves.cpu().pin_memory()
+            root = np.empty(4, dtype=np.uint64)
+            n_ = host.shape[0]
+
+            def once():
+                h = cl.C.c_void_p()
+                L.check(L.cuzk_tree_build(host.data_ptr(), n_, arity, 1, sp, cl.C.byref(h)), "tree_build")
+                L.check(L.cuzk_tree_root(h, root.ctypes.data, 1, sp), "tree_root")
+                L.check(L.cuzk_tree_free(h), "tree_free")
+
+            once()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                once()
+            dt = (time.perf_counter() - t0) / reps
+            return {"e2e_build_ms": dt * 1e3, "e2e_leaves_per_s": n_ / dt, "h2d_bytes": 32 * n_, "d2h_bytes": 32,
+                    "api": "cuzk_tree_build(mem=CUZK_MEM_HOST, pinned) + cuzk_tree_root"}
+
         if rank == 0:
             ms, leaves, levels = time_build(50_000, 2, 5)
             t = api.CudaNaryMerkleTree(arity=2)
@@ -374,6 +396,7 @@ def main():
             vms = a0.elapsed_time(a1) / 5
             merkle["binary_50k"] = {"leaves": 50_000, "arity": 2, "build_ms": ms, "leaves_per_s": 50_000 / (ms * 1e-3),
                                     "verify_5k_ms": vms, "proofs_per_s": 5000 / (vms * 1e-3), "all_valid": bool(res.all())}
+            merkle["binary_50k"].update(time_build_e2e(leaves, 2, 5))
             if world == 1 and not args.no_cpu:
                 merkle["binary_50k"]["cpu_reference"] = cpu_merkle_baseline(levels[-1].cpu().numpy().view(np.uint64).reshape(-1))
             ms, leaves, levels = time_build(1 << 20, 4, 3)
@@ -390,6 +413,7 @@ def main():
             vms = a0.elapsed_time(a1)
             merkle["quaternary_2p20"] = {"leaves": 1 << 20, "arity": 4, "build_ms": ms, "leaves_per_s": (1 << 20) / (ms * 1e-3),
                                          "verify_full_batch_ms": vms, "proofs_per_s": (1 << 20) / (vms * 1e-3), "all_valid": bool(res.all())}
+            merkle["quaternary_2p20"].update(time_build_e2e(leaves, 4, 3))
             del leaves, levels, pb, t
         # 8-ary 2^k-leaf build sharded as subtrees across the ranks, one NCCL all-gather of subtree roots (strong scaling)
         nleaves = 1 << args.merkle_log2

@@ -481,6 +481,7 @@ struct cuzk_tree {
   size_t n = 0, padded = 0, total = 0, nlevels = 0;
   unsigned arity = 0;
   int device = 0;
+  cudaStream_t stream = nullptr;   // the stream the tree was built on; the levels are returned to the pool in its order
 };
 
 int cuzk_tree_build(const uint64_t *leaves, size_t n, unsigned arity, int mem, void *stream, cuzk_tree_t **out) {
@@ -499,8 +500,10 @@ int cuzk_tree_build(const uint64_t *leaves, size_t n, unsigned arity, int mem, v
   t->nlevels = cuzk_merkle_num_levels(n, arity);
   t->device = g_device;
   cudaStream_t st = S(stream);
-  cudaError_t e = cudaMalloc(&t->levels, t->total * 32);
-  if (e != cudaSuccess) { delete t; return cuda_fail(e, "cudaMalloc(tree levels)"); }
+  t->stream = st;
+  // stream-ordered pool allocation: repeated builds reuse the pool's memory without a device-wide synchronisation
+  cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&t->levels), t->total * 32, st);
+  if (e != cudaSuccess) { delete t; return cuda_fail(e, "cudaMallocAsync(tree levels)"); }
   if (mem == CUZK_MEM_DEVICE) {
     rc = merkle_build_dev(leaves, n, arity, t->levels, st);
   } else {
@@ -512,7 +515,7 @@ int cuzk_tree_build(const uint64_t *leaves, size_t n, unsigned arity, int mem, v
     }
   }
   if (rc) {
-    cudaFree(t->levels);
+    cudaFreeAsync(t->levels, st);
     delete t;
     return rc;
   }
@@ -522,9 +525,9 @@ int cuzk_tree_build(const uint64_t *leaves, size_t n, unsigned arity, int mem, v
 
 int cuzk_tree_free(cuzk_tree_t *t) {
   if (!t) return CUZK_OK;
-  cudaError_t e = cudaFree(t->levels);
+  cudaError_t e = cudaFreeAsync(t->levels, t->stream);   // ordered after the work already enqueued on the tree's stream
   delete t;
-  if (e != cudaSuccess) return cuda_fail(e, "cudaFree(tree levels)");
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFreeAsync(tree levels)");
   return CUZK_OK;
 }
 
@@ -691,20 +694,20 @@ int cuzk_tree_append_leaves(cuzk_tree_t *t, const uint64_t *values, size_t count
   cudaMemcpyAsync(static_cast<char *>(all) + t->n * 32, dv, count * 32, cudaMemcpyDeviceToDevice, st);
   const size_t total2 = cuzk_merkle_total_nodes(n2, t->arity);
   uint64_t *levels2 = nullptr;
-  if ((e = cudaMalloc(&levels2, total2 * 32)) != cudaSuccess) {
+  if ((e = cudaMallocAsync(reinterpret_cast<void **>(&levels2), total2 * 32, st)) != cudaSuccess) {
     cudaFreeAsync(all, st);
     cudaFreeAsync(dv, st);
-    return cuda_fail(e, "cudaMalloc(tree levels)");
+    return cuda_fail(e, "cudaMallocAsync(tree levels)");
   }
   rc = merkle_build_dev(static_cast<const uint64_t *>(all), n2, t->arity, levels2, st);
   cudaFreeAsync(all, st);
   cudaFreeAsync(dv, st);
   if ((e = cudaStreamSynchronize(st)) != cudaSuccess && !rc) rc = cuda_fail(e, "cudaStreamSynchronize");
   if (rc) {
-    cudaFree(levels2);
+    cudaFreeAsync(levels2, st);
     return rc;
   }
-  cudaFree(t->levels);
+  cudaFreeAsync(t->levels, st);
   t->levels = levels2;
   t->n = n2;
   t->padded = cuzk_merkle_padded_leaves(n2, t->arity);

@@ -156,6 +156,8 @@ int cuzk_merkle_verify_batch(const uint64_t *leaf_values, const uint64_t *siblin
 typedef struct cuzk_tree cuzk_tree_t;
 /* CudaNaryMerkleTree::build_tree; n >= 1; `mem` describes `leaves` */
 int cuzk_tree_build(const uint64_t *leaves, size_t n, unsigned arity, int mem, void *stream, cuzk_tree_t **tree_out);
+/* returns the levels to the memory pool in the order of the stream the tree was built on (no device-wide synchronisation);
+ * work that uses the tree on OTHER streams must have completed */
 int cuzk_tree_free(cuzk_tree_t *tree);
 size_t cuzk_tree_leaf_count(const cuzk_tree_t *tree);
 size_t cuzk_tree_num_levels(const cuzk_tree_t *tree);
