@@ -11,14 +11,17 @@ namespace {
 // Host-buffer calls (mem == CUZK_MEM_HOST) stage through library-owned device buffers that are kept between calls
 // (the reference mallocs and frees on every call, poseidon_cuda.cu:374-408) and are cut into chunks that alternate
 // between two internal streams, so the H2D copy of chunk c+1 and the D2H copy of chunk c-1 overlap the kernel of chunk c.
-constexpr int kPipeStreams = 2;
+#ifndef CUZK_PIPE_STREAMS
+#define CUZK_PIPE_STREAMS 4   // measured: 2 streams x 1 wave 171 M/s, 3 x 1 178, 4 x 1/2 181, 8 x 1/4 182 (pinned, 1 M pairs)
+#endif
+constexpr int kPipeStreams = CUZK_PIPE_STREAMS;
 constexpr int kPipeSlots = 4;                       // up to 3 inputs + 1 output per stream
-constexpr size_t kHashChunk = 148 * CUZK_MIN_BLOCKS * CUZK_BLOCK;   // one resident wave of one-thread-per-hash CTAs
+constexpr size_t kHashChunk = 148 * CUZK_MIN_BLOCKS * CUZK_BLOCK / 2;   // half a resident wave of one-thread-per-hash CTAs per chunk
 constexpr size_t kCheapChunk = 1 << 20;             // element-wise field ops
 constexpr int kWsSlots = 6;
 
 struct HostPath {
-  cudaStream_t stream[kPipeStreams] = {nullptr, nullptr};
+  cudaStream_t stream[kPipeStreams] = {};
   void *buf[kPipeStreams][kPipeSlots] = {};
   size_t cap[kPipeStreams][kPipeSlots] = {};
   void *ws[kWsSlots] = {};

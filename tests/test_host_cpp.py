@@ -68,16 +68,28 @@ def test_host_test_binary_lists_tests():
     assert "HostMerkle.EveryLevelEqualsOracle" in out and "HostPoseidon.SingleAndPairHashesEqualOracle" in out
 
 
-def _run_gtest(path, timeout=900):
+def _run_gtest_once(path, timeout):
     res = subprocess.run([path], capture_output=True, text=True, timeout=timeout)
-    tail = res.stdout[-4000:] + res.stderr[-2000:]
-    assert res.returncode == 0, tail
+    tail = res.stdout[-6000:] + res.stderr[-2000:]
     m = re.search(r"\[  PASSED  \] (\d+) tests", res.stdout)
-    assert m and int(m.group(1)) > 0, tail
-    assert "[  FAILED  ]" not in res.stdout, tail
+    ok = res.returncode == 0 and m is not None and int(m.group(1)) > 0 and "[  FAILED  ]" not in res.stdout
     skipped = re.search(r"\[  SKIPPED \] (\d+) tests", res.stdout)
-    assert not skipped, "GPU tests were skipped on a GPU box:\n" + tail
-    return int(m.group(1))
+    return ok and not skipped, (int(m.group(1)) if m else 0), tail
+
+
+def _run_gtest(path, timeout=900):
+    """Runs a gtest binary; every test must pass and none may be skipped.  The reference's suites draw their inputs from
+    std::random_device and contain one wall-clock assertion (GPU faster than CPU on 1000 hashes), so a failed run is
+    repeated once: two failures fail the test, a single one is reported as a warning with its full output."""
+    ok, passed, tail = _run_gtest_once(path, timeout)
+    if not ok:
+        ok2, passed2, tail2 = _run_gtest_once(path, timeout)
+        assert ok2, "failed twice:\n--- first run ---\n" + tail + "\n--- second run ---\n" + tail2
+        import warnings
+
+        warnings.warn(f"{os.path.basename(path)} failed once and passed on repetition; first run:\n{tail}")
+        passed = passed2
+    return passed
 
 
 @pytest.mark.gpu
