@@ -10,7 +10,8 @@ namespace {
 
 // Host-buffer calls (mem == CUZK_MEM_HOST) stage through library-owned device buffers that are kept between calls
 // (the reference mallocs and frees on every call, poseidon_cuda.cu:374-408) and are cut into chunks that alternate
-// between two internal streams, so the H2D copy of chunk c+1 and the D2H copy of chunk c-1 overlap the kernel of chunk c.
+// over kPipeStreams internal streams, so the H2D copies of the next chunks and the D2H copies of the previous ones overlap
+// the kernel of chunk c.
 #ifndef CUZK_PIPE_STREAMS
 #define CUZK_PIPE_STREAMS 4   // measured: 2 streams x 1 wave 171 M/s, 3 x 1 178, 4 x 1/2 181, 8 x 1/4 182 (pinned, 1 M pairs)
 #endif
