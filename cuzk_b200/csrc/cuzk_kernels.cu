@@ -279,7 +279,7 @@ int cuzk_debug_fast_ops(int op, const uint64_t *a, const uint64_t *b, uint64_t *
 int cuzk_poseidon_sponge(const uint64_t *in, size_t width, uint64_t ds, uint64_t *out, size_t n, int mem, void *stream) {
   int rc = require_init();
   if (rc) return rc;
-  if (width > 64) return fail(CUZK_ERR_INVALID, "sponge width must be <= 64");
+  if (width > ((size_t)1 << 20)) return fail(CUZK_ERR_INVALID, "sponge width must be <= 2^20");
   if (n == 0) return CUZK_OK;
   if (!out || (width && !in)) return fail(CUZK_ERR_INVALID, "null pointer");
   auto run = [&](cudaStream_t st, const void *din, void *dout, size_t m) {

@@ -81,7 +81,7 @@ int cuzk_poseidon_hash_pairs(const uint64_t *left, const uint64_t *right, uint64
 /* batch_permutation (:39): in-place PoseidonHash::permutation on n states of 3 elements (poseidon.cpp:60-87) */
 int cuzk_poseidon_permutation(uint64_t *states, size_t n, int mem, void *stream);
 /* out[i] = PoseidonHash::sponge(in[i*width .. i*width+width-1], FieldElement(domain_sep))  (poseidon.cpp:103-126);
- * domain_sep 3 = hash_multiple (:98-101) = device_hash_n (src/poseidon/cuda/poseidon_cuda.cu:118-142). width <= 64. */
+ * domain_sep 3 = hash_multiple (:98-101) = device_hash_n (src/poseidon/cuda/poseidon_cuda.cu:118-142). width <= 2^20. */
 int cuzk_poseidon_sponge(const uint64_t *in, size_t width, uint64_t domain_sep, uint64_t *out, size_t n, int mem,
                          void *stream);
 /* round constants (192 x 4 limbs) and MDS matrix (9 x 4 limbs) as the library uses them; host output.

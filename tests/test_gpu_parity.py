@@ -667,3 +667,14 @@ def test_device_tree_append_equals_fresh_build(gpu, oracle, arity):
         res = t.verify_batch_proofs(pb, to_dev(cur[idx.astype(np.int64)]) if dev else cur[idx.astype(np.int64)])
         assert bool((res.cpu().numpy() if dev else res).all())
         t.close()
+
+
+def test_long_sponges(gpu, oracle):
+    """hash_multiple over long inputs (the reference's sponge has no length limit): widths 65, 200 and 1001, host and device."""
+    h = gpu.CudaPoseidonHash()
+    rng = np.random.default_rng(65)
+    for width, n in ((65, 40), (200, 12), (1001, 3)):
+        x = rnd(rng, width * n, False)
+        want = oracle.sponge(x, width, 3)
+        assert (h.batch_sponge(x, width, 3) == want).all(), width
+        assert (to_host(h.batch_sponge(to_dev(x), width, 3)) == want).all(), width
