@@ -130,20 +130,6 @@ __device__ __forceinline__ void mds_exact(u32 (&s0)[8], u32 (&s1)[8], u32 (&s2)[
 // The wrap bit w_ij = [low >= W - h*k] is decided from the top word of low; the two cases where the top
 // word cannot decide (carry into word 7 ambiguous, or low_7 equal to the threshold word; ~2^-27 per term)
 // set `unc` and the caller recomputes the layer with mds_exact.
-#define CUZK_NP0 (0u - CUZK_P0)
-#define CUZK_NP1 (~CUZK_P1)
-#define CUZK_NP2 (~CUZK_P2)
-#define CUZK_NP3 (~CUZK_P3)
-#define CUZK_NP4 (~CUZK_P4)
-#define CUZK_NP5 (~CUZK_P5)
-#define CUZK_NP6 (~CUZK_P6)
-#define CUZK_NP7 (~CUZK_P7)
-__host__ __device__ constexpr u32 np_limb(int i) {   // limbs of W - p (P0 != 0, so no borrow past limb 0)
-  const u32 v[8] = {CUZK_NP0, CUZK_NP1, CUZK_NP2, CUZK_NP3, CUZK_NP4, CUZK_NP5, CUZK_NP6, CUZK_NP7};
-  return v[i];
-}
-constexpr u32 kQuotMagic = (u32)((1ull << 61) / (u64)(CUZK_P7 + 1u));   // floor(2^61 / (p_top + 1))
-
 // wrap bit of one term: adds w to wsum, ORs the "cannot decide" conditions into unc
 template <u32 C>
 __device__ __forceinline__ void mds_wrap_bit(u32 &wsum, u32 &unc, const u32 (&s)[8]) {
