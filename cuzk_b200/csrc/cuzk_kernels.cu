@@ -86,6 +86,11 @@ int cuzk_debug_set_fuse(int mode) {
   g_fuse_mode = mode > 0 ? 1 : 0;
   return old;
 }
+size_t cuzk_debug_set_coop_max(size_t units) {
+  const size_t old = g_coop_max;
+  g_coop_max = units;
+  return old;
+}
 uint64_t cuzk_debug_fallback_count(void) {
   unsigned long long v = 0;
   if (cudaMemcpyFromSymbol(&v, g_exact_fallbacks, sizeof v) != cudaSuccess) return ~0ull;
@@ -214,6 +219,10 @@ int cuzk_poseidon_hash_single(const uint64_t *in, uint64_t *out, size_t n, int m
   if (n == 0) return CUZK_OK;
   if (!in || !out) return fail(CUZK_ERR_INVALID, "null pointer");
   auto run = [](cudaStream_t st, const void *din, void *dout, size_t m) {
+    if (use_coop(m)) {
+      coop_hash_single_kernel<<<coop_grid(m), kCoopBlock, 0, st>>>(static_cast<const uint4 *>(din), static_cast<uint4 *>(dout), m);
+      return check_launch("coop_hash_single_kernel");
+    }
     hash_single_kernel<<<grid_for(m, kBlock), kBlock, 0, st>>>(static_cast<const uint4 *>(din), static_cast<uint4 *>(dout), m);
     return check_launch("hash_single_kernel");
   };
@@ -230,6 +239,11 @@ int cuzk_poseidon_hash_pairs(const uint64_t *left, const uint64_t *right, uint64
   if (n == 0) return CUZK_OK;
   if (!left || !right || !out) return fail(CUZK_ERR_INVALID, "null pointer");
   auto run = [](cudaStream_t st, const void *dl, const void *dr, void *dout, size_t m) {
+    if (use_coop(m)) {
+      coop_hash_pairs_kernel<<<coop_grid(m), kCoopBlock, 0, st>>>(static_cast<const uint4 *>(dl), static_cast<const uint4 *>(dr),
+                                                              static_cast<uint4 *>(dout), m);
+      return check_launch("coop_hash_pairs_kernel");
+    }
     hash_pairs_kernel<<<grid_for(m, kBlock), kBlock, 0, st>>>(static_cast<const uint4 *>(dl), static_cast<const uint4 *>(dr),
                                                              static_cast<uint4 *>(dout), m);
     return check_launch("hash_pairs_kernel");
@@ -247,6 +261,10 @@ int cuzk_poseidon_permutation(uint64_t *states, size_t n, int mem, void *stream)
   if (n == 0) return CUZK_OK;
   if (!states) return fail(CUZK_ERR_INVALID, "null pointer");
   auto run = [](cudaStream_t st, void *d, size_t m) {
+    if (use_coop(m)) {
+      coop_permutation_kernel<<<coop_grid(m), kCoopBlock, 0, st>>>(static_cast<uint4 *>(d), m);
+      return check_launch("coop_permutation_kernel");
+    }
     permutation_kernel<<<grid_for(m, kBlock), kBlock, 0, st>>>(static_cast<uint4 *>(d), m);
     return check_launch("permutation_kernel");
   };
@@ -283,6 +301,11 @@ int cuzk_poseidon_sponge(const uint64_t *in, size_t width, uint64_t ds, uint64_t
   if (n == 0) return CUZK_OK;
   if (!out || (width && !in)) return fail(CUZK_ERR_INVALID, "null pointer");
   auto run = [&](cudaStream_t st, const void *din, void *dout, size_t m) {
+    if (use_coop(m) && width <= 0x7fffffffu) {
+      coop_sponge_kernel<<<coop_grid(m), kCoopBlock, 0, st>>>(static_cast<const uint4 *>(din), (int)width, (u32)ds, (u32)(ds >> 32),
+                                                          static_cast<uint4 *>(dout), m);
+      return check_launch("coop_sponge_kernel");
+    }
     sponge_kernel<<<grid_for(m, kBlock), kBlock, 0, st>>>(static_cast<const uint4 *>(din), (int)width, (u32)ds, (u32)(ds >> 32),
                                                          static_cast<uint4 *>(dout), m);
     return check_launch("sponge_kernel");
@@ -454,6 +477,13 @@ int cuzk_merkle_verify_batch(const uint64_t *leaf_values, const uint64_t *siblin
   if (!leaf_values || !root || !results_out || (levels && (!siblings || !positions))) return fail(CUZK_ERR_INVALID, "null pointer");
   cudaStream_t st = S(stream);
   if (mem == CUZK_MEM_DEVICE) {
+    if (use_coop(num_proofs)) {
+      coop_merkle_verify_kernel<<<coop_grid(num_proofs), kCoopBlock, 0, st>>>(reinterpret_cast<const uint4 *>(leaf_values),
+                                                                          reinterpret_cast<const uint4 *>(siblings), positions, (int)levels,
+                                                                          (int)arity, reinterpret_cast<const uint4 *>(root), uint4{}, uint4{},
+                                                                          results_out, num_proofs);
+      return check_launch("coop_merkle_verify_kernel");
+    }
     merkle_verify_kernel<<<grid_for(num_proofs, kBlock), kBlock, 0, st>>>(reinterpret_cast<const uint4 *>(leaf_values),
                                                                          reinterpret_cast<const uint4 *>(siblings), positions, (int)levels,
                                                                          (int)arity, reinterpret_cast<const uint4 *>(root), uint4{}, uint4{},
@@ -468,6 +498,12 @@ int cuzk_merkle_verify_batch(const uint64_t *leaf_values, const uint64_t *siblin
   // proofs are independent: chunk them like hashes (each costs levels x ceil(arity/2) permutations)
   return host_pipeline(num_proofs, kHashChunk, levels ? 3 : 1, ins, in_bytes, results_out, 1, false,
                        [&](cudaStream_t s2, void **d_in, void *d_out, size_t m) {
+                         if (use_coop(m)) {
+                           coop_merkle_verify_kernel<<<coop_grid(m), kCoopBlock, 0, s2>>>(
+                               static_cast<const uint4 *>(d_in[0]), static_cast<const uint4 *>(d_in[1]), static_cast<const u32 *>(d_in[2]),
+                               (int)levels, (int)arity, nullptr, root_lo, root_hi, static_cast<uint8_t *>(d_out), m);
+                           return check_launch("coop_merkle_verify_kernel");
+                         }
                          merkle_verify_kernel<<<grid_for(m, kBlock), kBlock, 0, s2>>>(
                              static_cast<const uint4 *>(d_in[0]), static_cast<const uint4 *>(d_in[1]), static_cast<const u32 *>(d_in[2]),
                              (int)levels, (int)arity, nullptr, root_lo, root_hi, static_cast<uint8_t *>(d_out), m);
@@ -643,7 +679,10 @@ int cuzk_tree_update_leaves(cuzk_tree_t *t, const uint64_t *indices, const uint6
   u64 divisor = 1;
   while (p > 1) {
     divisor *= t->arity;
-    merkle_update_level_kernel<<<grid_for(count, kBlock), kBlock, 0, st>>>(cur, cur + 2 * p, di, count, divisor, (int)t->arity);
+    if (use_coop(count))
+      coop_merkle_update_level_kernel<<<coop_grid(count), kCoopBlock, 0, st>>>(cur, cur + 2 * p, di, count, divisor, (int)t->arity);
+    else
+      merkle_update_level_kernel<<<grid_for(count, kBlock), kBlock, 0, st>>>(cur, cur + 2 * p, di, count, divisor, (int)t->arity);
     if ((rc = check_launch("merkle_update_level_kernel"))) return rc;
     cur += 2 * p;
     p /= t->arity;

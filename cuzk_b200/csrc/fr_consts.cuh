@@ -1,6 +1,6 @@
 // fr_consts.cuh -- BN254 scalar-field constants shared by the one-thread-per-unit path (fr.cuh) and the cooperative
-// eight-lanes-per-permutation path (octet.cuh).  Plain C++ (no device code) so the host-side lockstep emulation of the
-// cooperative path (tests/cpp/octet_emul.cpp) can include it too.
+// sixteen-lanes-per-permutation path (coop.cuh).  Plain C++ (no device code) so the host-side lockstep emulation of the
+// cooperative path (tests/cpp/coop_emul.cpp) can include it too.
 //   p : src/poseidon/field_arithmetic.cpp:12-14      k = 2^256 mod p : field_arithmetic.cpp:256-258
 #pragma once
 #include <cstdint>

@@ -86,6 +86,18 @@ int check_launch(const char *what) {
   return CUZK_OK;
 }
 
+// ---- cooperative (sixteen lanes per unit) dispatch ----------------------------------------------------------------------
+// A launch of the one-thread-per-unit kernels takes one permutation latency (~186 us) however few units it has; the
+// cooperative kernels (coop_kernels.cuh) take a fraction of that while they fit the chip at about one warp per SM
+// sub-partition (148 x 4 warps x 2 units) and lose to the one-thread kernels once their larger instruction stream per unit
+// fills the issue slots.  Launchers switch at g_coop_max units (cuzk_debug_set_coop_max; 0 = never).
+#ifndef CUZK_COOP_MAX_DEFAULT
+#define CUZK_COOP_MAX_DEFAULT 2368
+#endif
+size_t g_coop_max = CUZK_COOP_MAX_DEFAULT;
+inline bool use_coop(size_t units) { return units != 0 && units <= g_coop_max; }
+inline unsigned coop_grid(size_t units) { return grid_for(units * 16, kCoopBlock); }
+
 // ---- parallel host copies for pageable caller memory ----------------------------------------------------------------
 // cudaMemcpyAsync on pageable memory (a std::vector, which is what the reference's API hands us) is staged by the driver
 // through one thread at well under PCIe speed.  For such buffers the pipeline below stages through its own pinned bounce
@@ -360,7 +372,8 @@ int ensure_padding(unsigned arity, int need = 2) {
   }
   if (g_pad_levels[arity] >= need) return CUZK_OK;
   const int start = g_pad_levels[arity], end = std::min(kMaxPadLevels, std::max(need, start + 4));
-  padding_chain_kernel<<<1, 32>>>(reinterpret_cast<uint4 *>(d), (int)arity, start, end);
+  if (g_coop_max != 0) coop_padding_chain_kernel<<<1, 32>>>(reinterpret_cast<uint4 *>(d), (int)arity, start, end);
+  else padding_chain_kernel<<<1, 32>>>(reinterpret_cast<uint4 *>(d), (int)arity, start, end);
   int rc = check_launch("padding_chain_kernel");
   if (rc) return rc;
   CK(cudaMemcpy(g_h_pad[arity][start], d + 4 * start, (size_t)(end - start) * 32, cudaMemcpyDeviceToHost));
@@ -404,6 +417,11 @@ inline bool fuse_two_levels(size_t /*mid_nodes*/, size_t out_nodes, unsigned /*a
 
 int launch_level(const uint4 *in, uint4 *out, size_t in_real, size_t out_count, unsigned arity, const uint4 *pad_in, cudaStream_t st,
                  size_t ntrees = 1, size_t tree_stride = 0) {
+  if (use_coop(out_count * ntrees)) {
+    coop_merkle_level_kernel<<<coop_grid(out_count * ntrees), kCoopBlock, 0, st>>>(in, out, in_real, out_count, (int)arity, pad_in, pad_in + 2,
+                                                                               ntrees, tree_stride);
+    return check_launch("coop_merkle_level_kernel");
+  }
   merkle_level_kernel<<<grid_for(out_count * ntrees, kBlock), kBlock, 0, st>>>(in, out, in_real, out_count, (int)arity, pad_in, pad_in + 2,
                                                                                ntrees, tree_stride);
   return check_launch("merkle_level_kernel");

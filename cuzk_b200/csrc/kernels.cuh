@@ -417,3 +417,4 @@ __global__ void synth_u64_leaves_kernel(u64 *out, size_t n, u64 seed, u64 start)
   reinterpret_cast<ulonglong4 *>(out)[i] = make_ulonglong4(splitmix64_dev(seed, start + i), 0, 0, 0);
 }
 
+#include "coop_kernels.cuh"

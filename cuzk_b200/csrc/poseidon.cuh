@@ -384,6 +384,38 @@ __device__ __forceinline__ void set_small(u32 (&x)[8], u32 v) {
 // absorbs two per permutation, a final odd input alone; width == 0 -> zero permutations -> output 0.
 // `load(x, i)` must be repeatable: when the fast pass reports an undecided comparison the whole sponge is evaluated
 // again on the exact path.
+// the whole sponge on the exact path (the reference's evaluation order, step by step): the fallback of every fast path
+template <class Loader>
+__device__ __forceinline__ void sponge_exact(u32 (&out)[8], u32 ds_lo, u32 ds_hi, int width, Loader load) {
+  atomicAdd(&g_exact_fallbacks, 1ull);
+  u32 st[24];
+#pragma unroll
+  for (int i = 0; i < 24; ++i) st[i] = 0;
+  st[0] = ds_lo;
+  st[1] = ds_hi;
+#pragma unroll 1
+  for (int i = 0; i < width; i += 2) {
+    u32 x[8], a[8];
+    load(x, i);
+#pragma unroll
+    for (int w = 0; w < 8; ++w) a[w] = st[8 + w];
+    absorb(a, x);
+#pragma unroll
+    for (int w = 0; w < 8; ++w) st[8 + w] = a[w];
+    if (i + 1 < width) {
+      load(x, i + 1);
+#pragma unroll
+      for (int w = 0; w < 8; ++w) a[w] = st[16 + w];
+      absorb(a, x);
+#pragma unroll
+      for (int w = 0; w < 8; ++w) st[16 + w] = a[w];
+    }
+    permute_exact(st, 1);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) out[i] = st[8 + i];
+}
+
 template <class Loader>
 __device__ __forceinline__ void sponge_n(u32 (&out)[8], u32 ds_lo, u32 ds_hi, int width, Loader load) {
   u32 unc = 0;
@@ -407,35 +439,7 @@ __device__ __forceinline__ void sponge_n(u32 (&out)[8], u32 ds_lo, u32 ds_hi, in
 #pragma unroll
     for (int i = 0; i < 8; ++i) out[i] = s1[i];
   }
-  if (unc != 0) {   // ~1e-6 per permutation on random data
-    atomicAdd(&g_exact_fallbacks, 1ull);
-    u32 st[24];
-#pragma unroll
-    for (int i = 0; i < 24; ++i) st[i] = 0;
-    st[0] = ds_lo;
-    st[1] = ds_hi;
-#pragma unroll 1
-    for (int i = 0; i < width; i += 2) {
-      u32 x[8], a[8];
-      load(x, i);
-#pragma unroll
-      for (int w = 0; w < 8; ++w) a[w] = st[8 + w];
-      absorb(a, x);
-#pragma unroll
-      for (int w = 0; w < 8; ++w) st[8 + w] = a[w];
-      if (i + 1 < width) {
-        load(x, i + 1);
-#pragma unroll
-        for (int w = 0; w < 8; ++w) a[w] = st[16 + w];
-        absorb(a, x);
-#pragma unroll
-        for (int w = 0; w < 8; ++w) st[16 + w] = a[w];
-      }
-      permute_exact(st, 1);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) out[i] = st[8 + i];
-  }
+  if (unc != 0) sponge_exact(out, ds_lo, ds_hi, width, load);   // ~1e-6 per permutation on random data
 }
 template <class Loader>
 __device__ __forceinline__ void sponge_n(u32 (&out)[8], u32 ds, int width, Loader load) {

@@ -203,6 +203,11 @@ int cuzk_debug_mds_layer(uint64_t *states, size_t n, int mode, void *stream);
  * default.  Returns the previous mode.  Results are identical in both modes. */
 int cuzk_debug_set_fuse(int mode);
 
+/* Launches of at most `units` units (hashes, nodes, proofs, states) run on the cooperative kernels -- sixteen lanes per
+ * permutation (csrc/coop.cuh), a fraction of the one-thread kernels' latency while the chip is not full -- larger ones on
+ * the one-thread-per-unit kernels.  0 = never cooperative.  Returns the previous threshold.  Results are identical. */
+size_t cuzk_debug_set_coop_max(size_t units);
+
 /* how many units (hashes, nodes, proof levels, states) were evaluated a second time on the exact path because the fast
  * path met a comparison its top-word test could not decide (about 1e-6 per permutation on random data); a blocking read */
 uint64_t cuzk_debug_fallback_count(void);

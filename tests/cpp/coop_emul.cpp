@@ -1,10 +1,10 @@
-// octet_emul.cpp -- TEST INFRASTRUCTURE: runs the cooperative eight-lanes-per-permutation source (cuzk_b200/csrc/octet.cuh)
-// on the host, eight threads in lockstep standing in for the eight lanes of one octet (shuffles and votes go through a
+// coop_emul.cpp -- TEST INFRASTRUCTURE: runs the cooperative sixteen-lanes-per-permutation source (cuzk_b200/csrc/coop.cuh)
+// on the host, sixteen threads in lockstep standing in for the lanes of one group (shuffles and votes go through a
 // shared exchange buffer and a spinning barrier), and compares every result with the plain-C oracle.  It checks the
 // arithmetic of the cooperative path -- in particular that a unit whose `unc` vote is clear is bit-exact -- without a GPU.
 //
-// usage: octet_emul [units] [seed] [plain]      exit code 0 = no unflagged mismatch
-#define CUZK_OCTET_HOST_EMUL 1
+// usage: coop_emul [units] [seed] [plain]      exit code 0 = no unflagged mismatch
+#define CUZK_COOP_HOST_EMUL 1
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -12,7 +12,7 @@
 #include <thread>
 #include <vector>
 
-#include "../../cuzk_b200/csrc/octet.cuh"
+#include "../../cuzk_b200/csrc/coop.cuh"
 
 extern "C" {
 void cuzk_oracle_round_constants(uint64_t *out);
@@ -24,7 +24,7 @@ void cuzk_oracle_batch_mds_layer(uint64_t *states, size_t n);
 }
 
 namespace {
-constexpr int kLanes = 8;
+constexpr int kLanes = 16;
 thread_local uint32_t tl_lane;
 std::atomic<uint32_t> g_count{0};
 std::atomic<uint32_t> g_gen{0};
@@ -38,27 +38,25 @@ void barrier() {
     g_gen.store(gen + 1, std::memory_order_release);
   } else {
     while (g_gen.load(std::memory_order_acquire) == gen) {
-#if defined(__x86_64__)
-      __builtin_ia32_pause();
-#endif
+      std::this_thread::yield();   // more lanes than cores: give the others the CPU
     }
   }
 }
 }  // namespace
 
 namespace cuzk {
-namespace oct {
-u32 lane8() { return tl_lane; }
+namespace coop {
+u32 lane16() { return tl_lane; }
 u32 shfl(u32 x, u32 src) {
   const uint32_t par = tl_parity;
   tl_parity ^= 1u;
   g_slot[par][tl_lane] = x;
   std::atomic_thread_fence(std::memory_order_seq_cst);
   barrier();
-  const u32 v = g_slot[par][src & 7u];
+  const u32 v = g_slot[par][src & 15u];
   return v;
 }
-u32 ballot8(bool p) {
+u32 ballot16(bool p) {
   const uint32_t par = tl_parity;
   tl_parity ^= 1u;
   g_slot[par][tl_lane] = p ? 1u : 0u;
@@ -68,7 +66,7 @@ u32 ballot8(bool p) {
   for (int i = 0; i < kLanes; ++i) b |= (g_slot[par][i] & 1u) << i;
   return b;
 }
-}  // namespace oct
+}  // namespace coop
 }  // namespace cuzk
 
 using namespace cuzk;
@@ -144,45 +142,46 @@ struct Job {
 };
 std::vector<Job> g_jobs;
 
-inline u32 word_of(const uint64_t *el, u32 m) { return (u32)(el[m >> 1] >> (32 * (m & 1))); }
+inline u32 word_of(const uint64_t *el, u32 m) { return m < 8 ? (u32)(el[m >> 1] >> (32 * (m & 1))) : 0u; }
 inline void put_word(uint64_t *el, u32 m, u32 v) {
   // called by all lanes into distinct 32-bit halves: go through a u32 view to avoid read-modify-write races
-  reinterpret_cast<volatile u32 *>(el)[m] = v;
+  if (m < 8) reinterpret_cast<volatile u32 *>(el)[m] = v;
 }
 
 void lane_main(uint32_t lane) {
   tl_lane = lane;
-  const oct::Lane L = oct::make_lane();
+  const coop::Lane L = coop::make_lane();
   RcTable rct;
   for (auto &job : g_jobs) {
+    coop::Flags F;
     u32 unc = 0;
     if (job.kind == 0) {
       u32 a[1][8], b[1], r[1];
-      oct::gather(a[0], word_of(&job.in[0], lane));
+      coop::gather(a[0], word_of(&job.in[0], lane));
       b[0] = word_of(&job.in[4], lane);
-      oct::mulred<1>(r, a, b, L, unc);
+      coop::mulred<1>(r, a, b, L, F);
       put_word(job.out, lane, r[0]);
     } else if (job.kind == 1) {
       u32 a[1] = {word_of(&job.in[0], lane)}, b[1] = {word_of(&job.in[4], lane)}, r[1];
-      oct::add_reduce<1>(r, a, b, L, unc);
+      coop::add_reduce<1>(r, a, b, L, F);
       put_word(job.out, lane, r[0]);
     } else if (job.kind == 2) {
       u32 s[3] = {word_of(&job.in[0], lane), word_of(&job.in[4], lane), word_of(&job.in[8], lane)};
-      oct::permute(s, rct, L, unc);
+      coop::permute(s, rct, L, F);
       for (int i = 0; i < 3; ++i) put_word(job.out + 4 * i, lane, s[i]);
     } else if (job.kind == 3) {
       u32 out;
       const uint64_t *in = job.in.data();
-      const u32 vote = oct::sponge(out, 3u, 0u, job.width, rct, L, [&](int i) { return word_of(in + 4 * i, lane); });
+      const u32 vote = coop::sponge(out, 3u, 0u, job.width, rct, L, [&](int i) { return word_of(in + 4 * i, lane); });
       put_word(job.out, lane, out);
       unc = vote;
     } else {
       u32 s[3] = {word_of(&job.in[0], lane), word_of(&job.in[4], lane), word_of(&job.in[8], lane)};
       u32 rc[3] = {0, 0, 0};
-      oct::mds_arc(s, rc, false, L, unc);
+      coop::mds_arc(s, rc, false, L, F);
       for (int i = 0; i < 3; ++i) put_word(job.out + 4 * i, lane, s[i]);
     }
-    const u32 vote = oct::ballot8(unc != 0);
+    const u32 vote = coop::ballot16(unc != 0 || coop::flagged(F));
     if (lane == 0) job.unc = vote;
   }
 }
