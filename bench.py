@@ -27,6 +27,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 IMAD_PER_PERM = 48_576          # 240 x 164 + 576 x 16 multiply-adds per permutation
+IMAD_WIDE_PIPE_MODEL_PER_SM_CLK = 32.0   # 4 heavy-pipe cycles per warp IMAD.WIDE (profiles/r01_tuning_notes.md) = 32 lanes / SM / clock
+# root of the 2^26-leaf 8-ary tree over cuzk_synth_u64_leaves(seed 4): the same on 1, 2, 4 and 8 GPUs, and equal to the
+# single-GPU full build (tests/test_gpu_parity.py::test_config4_octary_2p26_sharded_equals_full_build)
+EXPECTED_ROOTS = {(26, 8): "0af40a4830624406744ebf70622802c7811231c8e2ce8c441c20c1c714f9c075"}
 BYTES_PER_PAIR_HASH = 96        # 2 x 32 B in + 32 B out
 N_PAIRS = 1_000_000
 REF_PUBLISHED_PAIR_HASHES_PER_S = 2_145_027   # BASELINE.md section 1 (reference README.md:134, A100)
@@ -43,6 +47,8 @@ def parse():
     ap.add_argument("--pairs", type=int, default=N_PAIRS)
     ap.add_argument("--no-merkle", action="store_true", help="skip the Merkle sub-benchmarks")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the configs[4] hashing sweep")
+    ap.add_argument("--sweep-max-log2", type=int, default=28)
     ap.add_argument("--merkle-log2", type=int, default=26, help="log2 leaves of the sharded 8-ary build")
     return ap.parse_args()
 
@@ -106,7 +112,8 @@ def cpu_merkle_baseline(gpu_root):
 
 
 def reference_arm(args):
-    """--impl reference: the reference's own CPU path on all host cores, same metric/unit/config."""
+    """--impl reference: the reference's own CPU path on all host cores, same metric and unit.  Each step is a BOUNDED SAMPLE
+    of the workload (the CPU rate does not depend on the batch size); the line says how many hashes a step really ran."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -121,6 +128,23 @@ def reference_arm(args):
     total_h = per_step * len(vals)
     total_t = sum(dt for _, dt in vals)
     value = total_h / total_t
+    # the reference's OWN benchmark loop, unmodified: one thread, Poseidon::benchmark_poseidon_pairs (poseidon.cpp:195-219,
+    # called by src/poseidon/test/benchmark.cpp:162-163) -- BASELINE.md section 2 row 1a
+    stock = None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from oracle_lib import Ref, have_ref
+
+        if have_ref():
+            n1 = 20_000
+            stock = {"value": Ref().benchmark_poseidon_pairs(n1), "unit": UNIT, "cores": 1, "hashes": n1,
+                     "what": "Poseidon::benchmark_poseidon_pairs (poseidon.cpp:195-219), the loop behind run_poseidon_benchmark.sh, one host thread"}
+    except Exception as e:  # noqa: BLE001
+        stock = {"unavailable": str(e)}
+    cfg = workload_config(args, args.gpus)
+    cfg["workload"] = (f"{per_step} Poseidon pair hashes per step on {cores} host threads: a bounded sample of the GPU arm's "
+                       f"{args.pairs}-pair step (the CPU rate is independent of the batch size)")
+    cfg["pairs_per_step"] = per_step
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -130,14 +154,16 @@ def reference_arm(args):
         "steps": args.steps,
         "warmup": args.warmup,
         "ms_per_step": 1e3 * total_t / len(vals),
+        "hashes_per_step": per_step,
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
         "dtype": "u32x8 (256-bit integers)",
         "data": "synthetic",
-        "config": workload_config(args, args.gpus),
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": f"{per_step} pair hashes per step on {cores} host threads (PoseidonHash::hash_pair), {len(vals)} steps"},
+        "reference_single_thread": stock,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -226,7 +252,7 @@ def main():
     import torch.distributed as dist
 
     from cuzk_b200 import api, lib as cl
-    from cuzk_b200.distributed import CudaOps, plan_merkle_shards, sharded_merkle_root
+    from cuzk_b200.distributed import shard_slice, sharded_all_valid
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -279,6 +305,7 @@ def main():
         peak[name] = v.value
     # the roofline denominator: the best rate any form of the 32x32->64 multiply-add reaches on this chip
     imad_peak = max(v for k, v in peak.items() if k.startswith("imad_wide"))
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -325,21 +352,81 @@ def main():
     e2e_value = world * n * e2e_steps / e2e_s
     e2e_ok = bool((ho.view(torch.int64)[:256] == sets[0][2][:256].cpu()).all()) if args.warmup + args.steps > 0 else True
 
-    # the reference harness shape: 245 synchronous host calls of <= 4096 pairs (poseidon_cuda_benchmarks.cpp:63-117)
-    b = 4096
+    # the same call on PAGEABLE host memory (numpy arrays = what a std::vector hands over; the library stages through its own
+    # pinned bounce buffers)
+    pl, pr = hl.numpy().copy(), hr.numpy().copy()
+    po = np.empty_like(pl)
+
+    def step_pageable():
+        L.check(L.cuzk_poseidon_hash_pairs(pl.ctypes.data, pr.ctypes.data, po.ctypes.data, n, 1, sp), "hash_pairs(pageable)")
+
+    step_pageable()
+    barrier()
     t0 = time.perf_counter()
-    done = 0
-    while done < n:
-        m = min(b, n - done)
-        L.check(L.cuzk_poseidon_hash_pairs(hl.data_ptr() + done * 32, hr.data_ptr() + done * 32, ho.data_ptr() + done * 32, m, 1, sp), "hash_pairs(host)")
-        done += m
-    torch.cuda.synchronize(dev)
-    b4096_value = world * n / max_over_ranks(time.perf_counter() - t0)
+    for _ in range(max(2, e2e_steps // 2)):
+        step_pageable()
+    pageable_value = world * n * max(2, e2e_steps // 2) / max_over_ranks(time.perf_counter() - t0)
+    pageable_ok = bool((po[:256] == ho.numpy()[:256]).all())
+
+    # the reference harness shape: 245 synchronous host calls of <= 4096 pairs (poseidon_cuda_benchmarks.cpp:63-117), on pinned
+    # and on pageable memory (the reference harness holds std::vectors)
+    def harness(ptr_l, ptr_r, ptr_o):
+        b = 4096
+        t0 = time.perf_counter()
+        done = 0
+        while done < n:
+            m = min(b, n - done)
+            L.check(L.cuzk_poseidon_hash_pairs(ptr_l + done * 32, ptr_r + done * 32, ptr_o + done * 32, m, 1, sp), "hash_pairs(host)")
+            done += m
+        torch.cuda.synchronize(dev)
+        return world * n / max_over_ranks(time.perf_counter() - t0)
+
+    b = 4096
+    harness(hl.data_ptr(), hr.data_ptr(), ho.data_ptr())
+    b4096_value = harness(hl.data_ptr(), hr.data_ptr(), ho.data_ptr())
+    b4096_pageable = harness(pl.ctypes.data, pr.ctypes.data, po.ctypes.data)
+    harness_ok = bool((po[-256:] == sets[0][2][-256:].cpu().numpy()).all())
+
+    # ---- configs[4]: single / pair / sponge(8) hashing sweep over 2^16 .. 2^28 inputs (whole job; each rank its slice) ----
+    sweep = None
+    if not args.no_sweep:
+        sweep = []
+        for lg in (16, 20, 24, 28):
+            if lg > args.sweep_max_log2:
+                continue
+            total = 1 << lg
+            lo, hi = shard_slice(total, rank, world)
+            m = hi - lo
+            x = torch.empty((m, 4), dtype=torch.int64, device=dev)
+            out = torch.empty((m, 4), dtype=torch.int64, device=dev)
+            L.check(L.cuzk_synth_elements(x.data_ptr(), m, 5, lo, 1, sp), "synth")
+            reps = max(1, min(10, (1 << 22) // max(m, 1)))
+
+            def timed(fn):
+                fn()
+                barrier()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record(stream)
+                for _ in range(reps):
+                    fn()
+                a1.record(stream)
+                barrier()
+                return max_over_ranks(a0.elapsed_time(a1) / reps)
+
+            row = {"log2_inputs": lg}
+            ms = timed(lambda: L.check(L.cuzk_poseidon_hash_single(x.data_ptr(), out.data_ptr(), m, 0, sp), "single"))
+            row["single_hashes_per_s"] = total / (ms * 1e-3)
+            ms = timed(lambda: L.check(L.cuzk_poseidon_hash_pairs(x.data_ptr(), x.data_ptr() + (m // 2) * 32, out.data_ptr(), m // 2, 0, sp), "pairs"))
+            row["pair_hashes_per_s"] = (total // 2) / (ms * 1e-3)
+            ms = timed(lambda: L.check(L.cuzk_poseidon_sponge(x.data_ptr(), 8, 3, out.data_ptr(), m // 8, 0, sp), "sponge"))
+            row["sponge8_hashes_per_s"] = (total // 8) / (ms * 1e-3)
+            row["sponge8_permutations_per_s"] = (total // 2) / (ms * 1e-3)
+            sweep.append(row)
+            del x, out
 
     # ---- Merkle sub-benchmarks ----
     merkle = {}
     if not args.no_merkle:
-        ops = CudaOps(dev)
 
         def time_build(nleaves, arity, reps):
             leaves = torch.empty((nleaves, 4), dtype=torch.int64, device=dev)
@@ -415,28 +502,91 @@ def main():
                                          "verify_full_batch_ms": vms, "proofs_per_s": (1 << 20) / (vms * 1e-3), "all_valid": bool(res.all())}
             merkle["quaternary_2p20"].update(time_build_e2e(leaves, 4, 3))
             del leaves, levels, pb, t
-        # 8-ary 2^k-leaf build sharded as subtrees across the ranks, one NCCL all-gather of subtree roots (strong scaling)
+        # config 3's full-batch verification, sharded: every rank verifies its contiguous slice of the 2^20 proofs (no data-path
+        # collective), the verdicts are ANDed with one all-reduce(MIN) of a byte
+        nq = 1 << 20
+        q0, q1 = shard_slice(nq, rank, world)
+        leaves4 = torch.empty((nq, 4), dtype=torch.int64, device=dev)
+        L.check(L.cuzk_synth_u64_leaves(leaves4.data_ptr(), nq, 3, 0, sp), "synth")
+        t4 = api.DeviceMerkleTree(leaves4, arity=4)
+        idx = torch.arange(q0, q1, device=dev, dtype=torch.int64)
+        pb = t4.generate_batch_proofs(idx)
+        lv = leaves4[q0:q1].contiguous()
+        res = t4.verify_batch_proofs(pb, lv)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        res = t4.verify_batch_proofs(pb, lv)
+        a1.record(stream)
+        barrier()
+        vms = max_over_ranks(a0.elapsed_time(a1))
+        all_ok = sharded_all_valid(res)
+        merkle["quaternary_2p20_sharded_verify"] = {"proofs": nq, "n_gpus": world, "verify_ms": vms, "proofs_per_s": nq / (vms * 1e-3),
+                                                    "all_valid": all_ok, "scaling": "strong",
+                                                    "collective": "none on the data path; verdicts: 1 x all_reduce(MIN) of one byte"}
+        t4.close()
+        del leaves4, pb, lv, res, idx
+
+        # 8-ary 2^k-leaf tree sharded as subtrees across the ranks THROUGH THE LIBRARY (cuzk_mg_*): every rank keeps all levels of
+        # its subtrees in HBM, one NCCL all-gather of 32-byte subtree roots issued by libcuzk_b200.so, top levels on every rank
+        # (strong scaling).  torch.distributed only carried the 128-byte NCCL id.
         nleaves = 1 << args.merkle_log2
-        plan = plan_merkle_shards(nleaves, 8, world)
-        l0, l1 = plan.rank_leaves(rank)
-        shard = torch.empty((max(l1 - l0, 1), 4), dtype=torch.int64, device=dev)
-        L.check(L.cuzk_synth_u64_leaves(shard.data_ptr(), l1 - l0, 4, l0, sp), "synth")
-        root = sharded_merkle_root(shard, plan, rank, ops)   # warm-up (also NCCL init)
+        mg = api.MultiGpu.from_torch_distributed(local)
+        l0, cnt = mg.shard_leaves(nleaves, 8, rank)
+        shard = torch.empty((max(cnt, 1), 4), dtype=torch.int64, device=dev)
+        L.check(L.cuzk_synth_u64_leaves(shard.data_ptr(), cnt, 4, l0, sp), "synth")
+        torch.cuda.synchronize(dev)
+        mg_stream = torch.cuda.ExternalStream(mg.stream(0), device=dev)
+        tree = mg.build_tree([shard], n=nleaves, arity=8)   # warm-up (also NCCL communicator bring-up)
+        tree.close()
         barrier()
         reps = 2
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record(stream)
-        for _ in range(reps):
-            root = sharded_merkle_root(shard, plan, rank, ops)
-        a1.record(stream)
+        a0.record(mg_stream)
+        for k in range(reps):
+            tree = mg.build_tree([shard], n=nleaves, arity=8)
+            if k + 1 < reps:
+                tree.close()
+        a1.record(mg_stream)
         barrier()
         ms = max_over_ranks(a0.elapsed_time(a1) / reps)
-        root_hex = "%064x" % sum(int(v) << (64 * i) for i, v in enumerate(root.cpu().numpy().view(np.uint64).reshape(-1)))
-        merkle["octary_sharded"] = {"leaves": nleaves, "arity": 8, "n_gpus": world, "subtree_height": plan.height,
-                                    "subtrees_per_rank": plan.per_rank, "build_ms": ms, "leaves_per_s": nleaves / (ms * 1e-3),
-                                    "scaling": "strong", "collective": "1 x all_gather_into_tensor of 32 B subtree roots",
-                                    "root": root_hex, "levels_stored": "subtree roots only"}
+        root = tree.get_root_hash()
+        root_hex = "%064x" % sum(int(v) << (64 * i) for i, v in enumerate(root))
+        expected = EXPECTED_ROOTS.get((args.merkle_log2, 8))
+        # proofs served from the levels the shards keep, for leaves of this rank, verified against the sharded root
+        nproofs = 16384 // world
+        rng = np.random.default_rng(1000 + rank)
+        pidx = (l0 + rng.integers(0, max(cnt, 1), nproofs)).astype(np.uint64)
+        t0 = time.perf_counter()
+        proofs = tree.generate_batch_proofs(pidx)
+        t1 = time.perf_counter()
+        vals = shard[torch.from_numpy((pidx - np.uint64(l0)).astype(np.int64)).to(dev)].cpu().numpy().view(np.uint64)
+        verdicts = tree.verify_batch_proofs(proofs, vals)
+        proofs_ok = sharded_all_valid(torch.from_numpy(verdicts).to(dev)) and bool((proofs.positions != 0xFFFFFFFF).all())
+        perms = sum((1 << (3 * k)) * 4 for k in range(args.merkle_log2 // 3))   # nodes x ceil(8 / 2) permutations
+        merkle["octary_sharded"] = {"leaves": nleaves, "arity": 8, "n_gpus": world, "subtree_height": tree.subtree_height,
+                                    "build_ms": ms, "leaves_per_s": nleaves / (ms * 1e-3),
+                                    "scaling": "strong", "collective": "1 x ncclAllGather of 32 B subtree roots, issued by libcuzk_b200.so (cuzk_mg_tree_build)",
+                                    "nccl_version": L.cuzk_mg_nccl_version(), "root": root_hex, "root_expected": expected,
+                                    "root_ok": (root_hex == expected) if expected else None,
+                                    "levels_stored": "every level of every subtree, on the GPU that owns it; top levels replicated",
+                                    "proofs_from_shards": {"proofs": nproofs * world, "all_valid": proofs_ok, "prove_ms_rank0": 1e3 * (t1 - t0)},
+                                    "roofline_frac": (perms / (ms * 1e-3)) * IMAD_PER_PERM / (imad_peak * world)}
+        if expected:
+            assert root_hex == expected, f"sharded root {root_hex} != expected {expected}"
+        assert proofs_ok, "a proof served from the sharded levels did not verify"
+        tree.close()
+        mg.close()
         del shard
+        # roofline fractions of the other Merkle configurations (SURVEY 8d convention: permutations x 48 576 multiply-adds)
+        if rank == 0:
+            def frac(perm_count, ms_):
+                return (perm_count / (ms_ * 1e-3)) * IMAD_PER_PERM / imad_peak
+            m2, m3 = merkle["binary_50k"], merkle["quaternary_2p20"]
+            m2["build_roofline_frac"] = frac(50_006, m2["build_ms"])           # real nodes of the 50 000-leaf binary tree, 1 permutation each
+            m2["verify_roofline_frac"] = frac(5000 * 16, m2["verify_5k_ms"])
+            m3["build_roofline_frac"] = frac(2 * 349_525, m3["build_ms"])      # (4^10 - 1) / 3 nodes, 2 permutations each
+            m3["verify_roofline_frac"] = frac((1 << 20) * 10 * 2, m3["verify_full_batch_ms"])
 
     clocks = None
     if rank == 0:
@@ -464,21 +614,30 @@ def main():
             "ms_per_step": ms_per_step,
             "higher_is_better": True,
             "scaling": "weak",
-            "vs_baseline": value / REF_PUBLISHED_PAIR_HASHES_PER_S,
-            "vs_baseline_note": "BASELINE.md: 2 145 027 pair hashes/s, the reference's CUDA path on an A100 through its 1 M-hash batch-4096 "
-                                "host-vector harness (README.md:134); the same harness shape here is e2e.reference_harness_batch4096",
+            "vs_baseline": b4096_pageable / REF_PUBLISHED_PAIR_HASHES_PER_S,
+            "vs_baseline_note": "like for like: BASELINE.md's 2 145 027 pair hashes/s is the reference's CUDA path on an A100 through its 1 M-hash "
+                                "batch-4096 host-vector harness (README.md:134); the numerator is the same harness shape here on pageable host "
+                                "memory (e2e.reference_harness_batch4096.pageable), not the device-resident `value`",
             "dtype": "u32x8 (256-bit integers, IMAD.WIDE carry chains)",
             "data": "synthetic",
             "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 64 * n, "d2h_bytes_per_step": 32 * n,
                     "api": "cuzk_poseidon_hash_pairs(mem=CUZK_MEM_HOST) on pinned host buffers", "steps": e2e_steps, "checked": e2e_ok,
-                    "reference_harness_batch4096": {"value": b4096_value, "unit": UNIT, "calls": -(-n // b)}},
+                    "pageable": {"value": pageable_value, "unit": UNIT, "checked": pageable_ok,
+                                 "api": "the same call on pageable memory (numpy / std::vector), staged by the library through pinned bounce buffers"},
+                    "reference_harness_batch4096": {"value": b4096_value, "pageable": b4096_pageable, "unit": UNIT, "calls": -(-n // b),
+                                                    "checked": harness_ok,
+                                                    "note": "245 synchronous host calls of <= 4096 pairs; each call runs on the cooperative kernels"}},
             "gpu_launches": int(launches),
             "roofline": {"bound": "imad", "kernel": "hash_pairs_kernel", "achieved": achieved / 1e12, "peak": imad_peak / 1e12,
                          "unit": "T multiply-adds/s (32x32->64)", "frac": achieved / imad_peak, "traffic": ncu_traffic(),
                          "algorithmic_bytes_per_launch": BYTES_PER_PAIR_HASH * n, "algorithmic_imad_per_launch": IMAD_PER_PERM * n,
                          "kernel_ms_per_launch": ms_per_step,
                          "peak_source": "measured in this run by cuzk_imad_peak: best of the IMAD.WIDE.U32 microbenchmarks (register / immediate / constant-bank multiplier, free and carry-chained), whole chip; MEASURED_PEAKS.json has no integer peak",
+                         "peak_pipe_model": {"imad_wide_per_sm_per_clk": IMAD_WIDE_PIPE_MODEL_PER_SM_CLK,
+                                             "per_s": IMAD_WIDE_PIPE_MODEL_PER_SM_CLK * sm_count * 1.965e9,
+                                             "frac_against_model": achieved / (IMAD_WIDE_PIPE_MODEL_PER_SM_CLK * sm_count * 1.965e9),
+                                             "note": "4 heavy-pipe cycles per warp IMAD.WIDE = 32 per SM per clock at 1965 MHz; the microbenchmark reaches 28.3 (its own sm__pipe_fmaheavy_cycles_active is in profiles/r02_imad_peak_ncu.txt)"},
                          "note": "achieved counts the reference's algorithmic multiply-adds (48 576 per permutation); the kernel executes fewer (symmetric squarings, MDS layer on the FP64 pipe), so frac can exceed 1 -- the multiplier's measured busy share is in profiles/*_ncu_summary.txt (sm__pipe_fmaheavy_cycles_active)",
                          "imad_per_hash": IMAD_PER_PERM, "pipe_microbench_per_s": peak,
                          "hbm": {"achieved_gbs": value / world * BYTES_PER_PAIR_HASH / 1e9, "peak_gbs": measured_hbm(),
@@ -486,6 +645,8 @@ def main():
             "cpu_baseline": cpu,
             "clocks": clocks,
             "merkle": merkle,
+            "sweep": sweep,
+            "sweep_note": "configs[4]: inputs over the whole job, device resident, each rank hashes its contiguous slice; hashes/s aggregate",
         }
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())

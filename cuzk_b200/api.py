@@ -494,3 +494,137 @@ class DeviceMerkleTree:
         self.leaf_count = lib.cuzk_tree_leaf_count(self._h)
         self.num_levels = lib.cuzk_tree_num_levels(self._h)
         self.total_nodes = lib.cuzk_tree_total_nodes(self._h)
+
+
+class MultiGpu:
+    """cuzk_mg_* handle: the hot path over several GPUs of one box, NCCL called from the library.
+
+    ``MultiGpu.local(ngpus)`` -- this process drives ``ngpus`` devices.
+    ``MultiGpu.from_torch_distributed()`` -- one process per GPU (torchrun): rank 0 creates the NCCL id, torch.distributed
+    only carries its 128 bytes to the other ranks; the collective itself (one all-gather of subtree roots per build) is
+    issued by the library."""
+
+    def __init__(self, handle, nranks: int, nlocal: int, first_rank: int):
+        self._h, self.nranks, self.nlocal, self.first_rank = handle, nranks, nlocal, first_rank
+
+    @classmethod
+    def local(cls, ngpus: int, devices=None) -> "MultiGpu":
+        import ctypes as C
+
+        lib = get_lib()
+        h = C.c_void_p()
+        arr = (C.c_int * ngpus)(*devices) if devices is not None else None
+        lib.check(lib.cuzk_mg_init_local(ngpus, arr, C.byref(h)), "cuzk_mg_init_local")
+        return cls(h, ngpus, ngpus, 0)
+
+    @classmethod
+    def from_torch_distributed(cls, device: int | None = None, group=None) -> "MultiGpu":
+        import ctypes as C
+
+        import torch.distributed as dist
+
+        lib = get_lib()
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        if device is None:
+            device = torch.cuda.current_device()
+        box = [None]
+        if world > 1:
+            if rank == 0:
+                buf = (C.c_uint8 * 128)()
+                lib.check(lib.cuzk_mg_unique_id(buf), "cuzk_mg_unique_id")
+                box[0] = bytes(buf)
+            dist.broadcast_object_list(box, src=0, group=group)
+        h = C.c_void_p()
+        idbuf = (C.c_uint8 * 128).from_buffer_copy(box[0]) if box[0] is not None else None
+        lib.check(lib.cuzk_mg_init_rank(rank, world, int(device), idbuf, C.byref(h)), "cuzk_mg_init_rank")
+        return cls(h, world, 1, rank)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            get_lib().cuzk_mg_free(self._h)
+            self._h = None
+
+    def device(self, local: int = 0) -> int:
+        return get_lib().cuzk_mg_device(self._h, local)
+
+    def stream(self, local: int = 0):
+        return get_lib().cuzk_mg_stream(self._h, local)
+
+    def shard_leaves(self, n: int, arity: int, rank: int) -> tuple[int, int]:
+        """[first, first + count) of the leaves that shard `rank` holds in an n-leaf tree"""
+        import ctypes as C
+
+        first, count = C.c_size_t(), C.c_size_t()
+        lib = get_lib()
+        lib.check(lib.cuzk_mg_shard_leaves(n, arity, self.nranks, rank, C.byref(first), C.byref(count)), "cuzk_mg_shard_leaves")
+        return first.value, count.value
+
+    def batch_hash_pairs(self, left, right) -> np.ndarray:
+        l, r = _elems(left), _elems(right)
+        if l.shape != r.shape:
+            raise CuzkError("left/right size mismatch")
+        out = np.empty_like(l)
+        lib = get_lib()
+        lib.check(lib.cuzk_mg_poseidon_hash_pairs(self._h, l.ctypes.data, r.ctypes.data, out.ctypes.data, l.shape[0]), "cuzk_mg_poseidon_hash_pairs")
+        return out
+
+    def build_tree(self, leaves, n: int | None = None, arity: int = 2) -> "ShardedMerkleTree":
+        """leaves: the whole leaf array in host memory (numpy), or a list with one int64 CUDA tensor per local device holding
+        that shard's leaves (``shard_leaves``); ``n`` (total leaf count) is needed in the second form."""
+        import ctypes as C
+
+        lib = get_lib()
+        h = C.c_void_p()
+        if isinstance(leaves, (list, tuple)):
+            if n is None:
+                raise CuzkError("n (total leaf count) is needed with per-device leaves")
+            ptrs = (C.c_void_p * self.nlocal)(*[(t.data_ptr() if t is not None and t.numel() else None) for t in leaves])
+            lib.check(lib.cuzk_mg_tree_build(self._h, ptrs, n, arity, MEM_DEVICE, C.byref(h)), "cuzk_mg_tree_build")
+        else:
+            x = _elems(leaves)
+            n = x.shape[0]
+            ptrs = (C.c_void_p * 1)(x.ctypes.data)
+            lib.check(lib.cuzk_mg_tree_build(self._h, ptrs, n, arity, MEM_HOST, C.byref(h)), "cuzk_mg_tree_build")
+        return ShardedMerkleTree(h, n, arity)
+
+
+class ShardedMerkleTree:
+    """cuzk_mg_tree_*: every GPU keeps all levels of its subtrees and serves proofs from them; the top levels are replicated."""
+
+    def __init__(self, handle, n: int, arity: int):
+        lib = get_lib()
+        self._h, self.leaf_count, self.arity = handle, n, arity
+        self.num_levels = lib.cuzk_mg_tree_num_levels(handle)
+        self.subtree_height = lib.cuzk_mg_tree_subtree_height(handle)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            get_lib().cuzk_mg_tree_free(self._h)
+            self._h = None
+
+    def get_root_hash(self) -> np.ndarray:
+        out = np.empty(4, dtype=np.uint64)
+        lib = get_lib()
+        lib.check(lib.cuzk_mg_tree_root(self._h, out.ctypes.data), "cuzk_mg_tree_root")
+        return out
+
+    def generate_batch_proofs(self, indices) -> MerkleProofBatch:
+        lib = get_lib()
+        L = self.num_levels - 1
+        idx = np.ascontiguousarray(indices, dtype=np.uint64)
+        sib = np.zeros((idx.size, L, self.arity - 1, 4), dtype=np.uint64)
+        pos = np.zeros((idx.size, L), dtype=np.uint32)
+        if idx.size and L:
+            lib.check(lib.cuzk_mg_tree_prove_batch(self._h, idx.ctypes.data, idx.size, sib.ctypes.data, pos.ctypes.data), "cuzk_mg_tree_prove_batch")
+        return MerkleProofBatch(sib, pos, idx, self.arity)
+
+    def verify_batch_proofs(self, proofs: MerkleProofBatch, leaf_values) -> np.ndarray:
+        lib = get_lib()
+        lv = _elems(leaf_values)
+        if lv.shape[0] != len(proofs):
+            raise CuzkError("size mismatch")
+        res = np.zeros(lv.shape[0], dtype=np.uint8)
+        if lv.shape[0]:
+            lib.check(lib.cuzk_mg_tree_verify_batch(self._h, lv.ctypes.data, proofs.siblings.ctypes.data, proofs.positions.ctypes.data,
+                                                    res.ctypes.data, lv.shape[0]), "cuzk_mg_tree_verify_batch")
+        return res

@@ -143,13 +143,18 @@ __global__ void __launch_bounds__(kCoopBlock) coop_merkle_level_kernel(const uin
 
 // incremental update, one level (see merkle_update_level_kernel)
 __global__ void __launch_bounds__(kCoopBlock) coop_merkle_update_level_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out,
-                                                                               const u64 *__restrict__ indices, size_t count, u64 divisor,
-                                                                               int arity) {
+                                                                               const u64 *__restrict__ indices, size_t count, size_t n,
+                                                                               u64 divisor, int arity) {
   const coop::Lane L = coop::make_lane();
   size_t q = coop_unit();
-  const bool active = q < count;
+  bool active = q < count;
   if (!active) q = count - 1;
-  const size_t node = indices[q] / divisor;
+  u64 idx = indices[q];
+  if (idx >= n) {   // out of range: skipped (the lanes stay in step on leaf 0)
+    active = false;
+    idx = 0;
+  }
+  const size_t node = idx / divisor;
   const uint4 *kids = in + 2 * node * (size_t)arity;
   coop_sponge_store(
       out + 2 * node, active, 3u, 0u, arity, L, [&](int j) { return ld_word(L, kids + 2 * j); },

@@ -1,6 +1,6 @@
-// host_path.cuh -- host-side machinery behind the C ABI (included once, by cuzk_kernels.cu): staging buffers and the chunked
-// double-buffered pipeline for host-buffer calls, the copy pool for pageable memory, padding constants, Merkle level
-// scheduling (per-level launches, grouped subtree passes on internal streams).
+// host_path.cuh -- host-side machinery behind the C ABI (included once, by cuzk_kernels.cu): the per-device context, staging
+// buffers and the chunked multi-stream pipeline for host-buffer calls, the copy pool for pageable memory, padding constants,
+// Merkle level scheduling (per-level launches, groups of subtrees on internal streams, cooperative kernels for narrow levels).
 #pragma once
 
 // ------------------------------------------------------------------------------------------------
@@ -20,16 +20,88 @@ constexpr int kPipeSlots = 4;                       // up to 3 inputs + 1 output
 constexpr size_t kHashChunk = 148 * CUZK_MIN_BLOCKS * CUZK_BLOCK / 2;   // half a resident wave of one-thread-per-hash CTAs per chunk
 constexpr size_t kCheapChunk = 1 << 20;             // element-wise field ops
 constexpr int kWsSlots = 6;
+constexpr int kSubtreeStreams = 4;
 
-struct HostPath {
+struct PinnedStage {   // per stream: pinned twins of the device staging buffers + "results are in the bounce buffer" event
+  void *buf[kPipeSlots] = {};
+  size_t cap[kPipeSlots] = {};
+  cudaEvent_t done = nullptr;
+};
+
+// Everything the library keeps on ONE device.  A process may initialise several devices (cuzk_init(d) for each); every
+// entry point runs on the calling thread's current CUDA device and uses that device's context (see CtxGuard).
+struct Ctx {
+  int device = -1;
+  int refcount = 0;
+  int sm_count = 148;
+  // padding constants E_l per arity on this device (the host copy g_h_pad is shared by all devices)
+  uint64_t *d_pad[9] = {nullptr};
+  int pad_levels[9] = {0};
+  std::mutex pad_mu;
+  // staging for host-buffer calls
   cudaStream_t stream[kPipeStreams] = {};
   void *buf[kPipeStreams][kPipeSlots] = {};
   size_t cap[kPipeStreams][kPipeSlots] = {};
   void *ws[kWsSlots] = {};
   size_t ws_cap[kWsSlots] = {};
-  bool ready = false;
-} g_hp;
-std::mutex g_hp_mu;   // host-buffer calls serialise on the staging buffers
+  bool hp_ready = false;
+  PinnedStage pin[kPipeStreams];
+  std::mutex hp_mu;   // host-buffer calls on one device serialise on its staging buffers
+  // internal streams for groups of subtrees
+  cudaStream_t sub_stream[kSubtreeStreams] = {};
+  cudaEvent_t sub_fork = nullptr, sub_join[kSubtreeStreams] = {};
+  std::mutex sub_mu;
+};
+constexpr int kMaxDevices = 32;
+Ctx g_ctx[kMaxDevices];
+
+// The context of the calling thread's current device.  When that device was never initialised but exactly one other device
+// was (the common single-GPU program whose worker threads never call cudaSetDevice), the call switches to it and restores
+// the caller's device on return: kernels, constants and staging buffers always belong to one and the same device.
+class CtxGuard {
+ public:
+  CtxGuard() {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); return; }
+    if (cur >= 0 && cur < kMaxDevices && g_ctx[cur].refcount > 0) { ctx_ = &g_ctx[cur]; return; }
+    int only = -1, count = 0;
+    for (int d = 0; d < kMaxDevices; ++d)
+      if (g_ctx[d].refcount > 0) { only = d; ++count; }
+    if (count == 1 && cudaSetDevice(only) == cudaSuccess) {
+      restore_ = cur;
+      ctx_ = &g_ctx[only];
+    }
+  }
+  explicit CtxGuard(int device) {   // run on `device` whatever the caller's current device is (tree handles, multi-GPU layer)
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); return; }
+    if (device < 0 || device >= kMaxDevices || g_ctx[device].refcount <= 0) return;
+    if (cur != device) {
+      if (cudaSetDevice(device) != cudaSuccess) return;
+      restore_ = cur;
+    }
+    ctx_ = &g_ctx[device];
+  }
+  ~CtxGuard() {
+    if (restore_ >= 0) cudaSetDevice(restore_);
+  }
+  CtxGuard(const CtxGuard &) = delete;
+  CtxGuard &operator=(const CtxGuard &) = delete;
+  Ctx *get() const { return ctx_; }
+
+ private:
+  Ctx *ctx_ = nullptr;
+  int restore_ = -1;
+};
+#define CUZK_NOT_INIT_MSG "cuzk_b200: library not initialised on the calling thread's CUDA device (call cuzk_init)"
+#define CUZK_CTX(c)                                          \
+  CtxGuard guard__;                                          \
+  if (!guard__.get()) return fail(CUZK_ERR_CUDA, CUZK_NOT_INIT_MSG); \
+  Ctx &c = *guard__.get()
+#define CUZK_CTX_ON(c, device)                               \
+  CtxGuard guard__(device);                                  \
+  if (!guard__.get()) return fail(CUZK_ERR_CUDA, CUZK_NOT_INIT_MSG); \
+  Ctx &c = *guard__.get()
 
 int hp_reserve(void *&p, size_t &cap, size_t bytes) {
   if (bytes <= cap) return CUZK_OK;
@@ -44,39 +116,38 @@ int hp_reserve(void *&p, size_t &cap, size_t bytes) {
   cap = want;
   return CUZK_OK;
 }
-int ws_get(int slot, size_t bytes, void **out) {
-  int rc = hp_reserve(g_hp.ws[slot], g_hp.ws_cap[slot], bytes ? bytes : 1);
-  *out = g_hp.ws[slot];
+int ws_get(Ctx &c, int slot, size_t bytes, void **out) {
+  int rc = hp_reserve(c.ws[slot], c.ws_cap[slot], bytes ? bytes : 1);
+  *out = c.ws[slot];
   return rc;
 }
-int hp_start() {
-  if (g_hp.ready) return CUZK_OK;
-  for (int i = 0; i < kPipeStreams; ++i) CK(cudaStreamCreateWithFlags(&g_hp.stream[i], cudaStreamNonBlocking));
-  g_hp.ready = true;
+int hp_start(Ctx &c) {
+  if (c.hp_ready) return CUZK_OK;
+  for (int i = 0; i < kPipeStreams; ++i) CK(cudaStreamCreateWithFlags(&c.stream[i], cudaStreamNonBlocking));
+  c.hp_ready = true;
   return CUZK_OK;
 }
-void hp_stop() {
+void hp_stop(Ctx &c) {
   for (int i = 0; i < kPipeStreams; ++i) {
     for (int j = 0; j < kPipeSlots; ++j) {
-      if (g_hp.buf[i][j]) cudaFree(g_hp.buf[i][j]);
-      g_hp.buf[i][j] = nullptr;
-      g_hp.cap[i][j] = 0;
+      if (c.buf[i][j]) cudaFree(c.buf[i][j]);
+      c.buf[i][j] = nullptr;
+      c.cap[i][j] = 0;
+      if (c.pin[i].buf[j]) cudaFreeHost(c.pin[i].buf[j]);
+      c.pin[i].buf[j] = nullptr;
+      c.pin[i].cap[j] = 0;
     }
-    if (g_hp.stream[i]) cudaStreamDestroy(g_hp.stream[i]);
-    g_hp.stream[i] = nullptr;
+    if (c.pin[i].done) cudaEventDestroy(c.pin[i].done);
+    c.pin[i].done = nullptr;
+    if (c.stream[i]) cudaStreamDestroy(c.stream[i]);
+    c.stream[i] = nullptr;
   }
   for (int j = 0; j < kWsSlots; ++j) {
-    if (g_hp.ws[j]) cudaFree(g_hp.ws[j]);
-    g_hp.ws[j] = nullptr;
-    g_hp.ws_cap[j] = 0;
+    if (c.ws[j]) cudaFree(c.ws[j]);
+    c.ws[j] = nullptr;
+    c.ws_cap[j] = 0;
   }
-  g_hp.ready = false;
-}
-void pin_stop();
-
-int require_init() {
-  if (g_refcount <= 0) return fail(CUZK_ERR_CUDA, "cuzk_b200: library not initialised (call cuzk_init)");
-  return CUZK_OK;
+  c.hp_ready = false;
 }
 
 int check_launch(const char *what) {
@@ -89,13 +160,13 @@ int check_launch(const char *what) {
 // ---- cooperative (sixteen lanes per unit) dispatch ----------------------------------------------------------------------
 // A launch of the one-thread-per-unit kernels takes one permutation latency (~186 us) however few units it has; the
 // cooperative kernels (coop_kernels.cuh) take a fraction of that while they fit the chip at about one warp per SM
-// sub-partition (148 x 4 warps x 2 units) and lose to the one-thread kernels once their larger instruction stream per unit
+// sub-partition (148 x 4 warps x 2 units; measured on B200: 94 us up to 1184 units, 116 at 2368, 148 at 3552, 189 at 4736 against 187 us) and lose to the one-thread kernels once their larger instruction stream per unit
 // fills the issue slots.  Launchers switch at g_coop_max units (cuzk_debug_set_coop_max; 0 = never).
 #ifndef CUZK_COOP_MAX_DEFAULT
-#define CUZK_COOP_MAX_DEFAULT 2368
+#define CUZK_COOP_MAX_DEFAULT 3552
 #endif
-size_t g_coop_max = CUZK_COOP_MAX_DEFAULT;
-inline bool use_coop(size_t units) { return units != 0 && units <= g_coop_max; }
+std::atomic<size_t> g_coop_max{CUZK_COOP_MAX_DEFAULT};
+inline bool use_coop(size_t units) { return units != 0 && units <= g_coop_max.load(std::memory_order_relaxed); }
 inline unsigned coop_grid(size_t units) { return grid_for(units * 16, kCoopBlock); }
 
 // ---- parallel host copies for pageable caller memory ----------------------------------------------------------------
@@ -110,8 +181,9 @@ class CopyPool {
       memcpy(dst, src, bytes);
       return;
     }
+    std::lock_guard<std::mutex> one_at_a_time(call_mu_);   // the contexts of several devices share the pool
     const int parts = (int)workers_.size() + 1;
-    const size_t slice = ((bytes / parts) + 4095) & ~(size_t)4095;
+    const size_t slice = (((bytes + parts - 1) / parts) + 4095) & ~(size_t)4095;   // parts * slice >= bytes
     {
       std::lock_guard<std::mutex> lk(mu_);
       dst_ = static_cast<char *>(dst);
@@ -137,6 +209,7 @@ class CopyPool {
 
  private:
   bool start() {
+    std::lock_guard<std::mutex> lk(call_mu_);
     if (started_) return !workers_.empty();
     started_ = true;
     unsigned hw = std::thread::hardware_concurrency();
@@ -163,7 +236,7 @@ class CopyPool {
     }
   }
   std::vector<std::thread> workers_;
-  std::mutex mu_;
+  std::mutex mu_, call_mu_;
   std::condition_variable cv_, done_cv_;
   char *dst_ = nullptr;
   const char *src_ = nullptr;
@@ -174,31 +247,14 @@ class CopyPool {
 };
 CopyPool g_copy_pool;
 
-struct PinnedStage {   // per stream: pinned twins of the device staging buffers + "results are in the bounce buffer" event
-  void *buf[kPipeSlots] = {};
-  size_t cap[kPipeSlots] = {};
-  cudaEvent_t done = nullptr;
-} g_pin[kPipeStreams];
-
 int pin_reserve(void *&p, size_t &cap, size_t bytes) {
   if (bytes <= cap) return CUZK_OK;
   if (p) CK(cudaFreeHost(p));
   p = nullptr;
   cap = 0;
-  CK(cudaHostAlloc(&p, bytes, cudaHostAllocDefault));
+  CK(cudaHostAlloc(&p, bytes, cudaHostAllocPortable));
   cap = bytes;
   return CUZK_OK;
-}
-void pin_stop() {
-  for (auto &st : g_pin) {
-    for (int j = 0; j < kPipeSlots; ++j) {
-      if (st.buf[j]) cudaFreeHost(st.buf[j]);
-      st.buf[j] = nullptr;
-      st.cap[j] = 0;
-    }
-    if (st.done) cudaEventDestroy(st.done);
-    st.done = nullptr;
-  }
 }
 bool is_pageable(const void *p) {
   cudaPointerAttributes attr;
@@ -211,35 +267,35 @@ bool is_pageable(const void *p) {
 
 // bulk copies between caller host memory and device memory on stream `st`; pageable memory goes through the pinned
 // bounce buffers in 8 MiB pieces filled / drained by the copy pool.  Both return with the copy complete or enqueued such
-// that `host` may be reused (upload) / read (download) by the caller.  Call with g_hp_mu held.
+// that `host` may be reused (upload) / read (download) by the caller.  Call with c.hp_mu held.
 constexpr size_t kBulkPiece = (size_t)8 << 20;
-int bulk_upload(void *dev, const void *host, size_t bytes, cudaStream_t st) {
+int bulk_upload(Ctx &c, void *dev, const void *host, size_t bytes, cudaStream_t st) {
   if (bytes < ((size_t)4 << 20) || !is_pageable(host)) {
     CK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, st));
     return CUZK_OK;
   }
   int rc;
   for (int s = 0; s < kPipeStreams; ++s) {
-    if ((rc = pin_reserve(g_pin[s].buf[0], g_pin[s].cap[0], kBulkPiece))) return rc;
-    if (!g_pin[s].done) CK(cudaEventCreateWithFlags(&g_pin[s].done, cudaEventDisableTiming));
+    if ((rc = pin_reserve(c.pin[s].buf[0], c.pin[s].cap[0], kBulkPiece))) return rc;
+    if (!c.pin[s].done) CK(cudaEventCreateWithFlags(&c.pin[s].done, cudaEventDisableTiming));
   }
   bool used[kPipeStreams] = {};
   size_t at = 0;
-  for (int c = 0; at < bytes; ++c) {
-    const int s = c % kPipeStreams;
+  for (int k = 0; at < bytes; ++k) {
+    const int s = k % kPipeStreams;
     const size_t m = std::min(kBulkPiece, bytes - at);
-    if (used[s]) CK(cudaEventSynchronize(g_pin[s].done));   // the piece that used this bounce buffer has left it
-    g_copy_pool.copy(g_pin[s].buf[0], static_cast<const char *>(host) + at, m);
-    CK(cudaMemcpyAsync(static_cast<char *>(dev) + at, g_pin[s].buf[0], m, cudaMemcpyHostToDevice, st));
-    CK(cudaEventRecord(g_pin[s].done, st));
+    if (used[s]) CK(cudaEventSynchronize(c.pin[s].done));   // the piece that used this bounce buffer has left it
+    g_copy_pool.copy(c.pin[s].buf[0], static_cast<const char *>(host) + at, m);
+    CK(cudaMemcpyAsync(static_cast<char *>(dev) + at, c.pin[s].buf[0], m, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(c.pin[s].done, st));
     used[s] = true;
     at += m;
   }
   for (int s = 0; s < kPipeStreams; ++s)
-    if (used[s]) CK(cudaEventSynchronize(g_pin[s].done));
+    if (used[s]) CK(cudaEventSynchronize(c.pin[s].done));
   return CUZK_OK;
 }
-int bulk_download(void *host, const void *dev, size_t bytes, cudaStream_t st) {
+int bulk_download(Ctx &c, void *host, const void *dev, size_t bytes, cudaStream_t st) {
   if (bytes < ((size_t)4 << 20) || !is_pageable(host)) {
     CK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -247,24 +303,24 @@ int bulk_download(void *host, const void *dev, size_t bytes, cudaStream_t st) {
   }
   int rc;
   for (int s = 0; s < kPipeStreams; ++s) {
-    if ((rc = pin_reserve(g_pin[s].buf[0], g_pin[s].cap[0], kBulkPiece))) return rc;
-    if (!g_pin[s].done) CK(cudaEventCreateWithFlags(&g_pin[s].done, cudaEventDisableTiming));
+    if ((rc = pin_reserve(c.pin[s].buf[0], c.pin[s].cap[0], kBulkPiece))) return rc;
+    if (!c.pin[s].done) CK(cudaEventCreateWithFlags(&c.pin[s].done, cudaEventDisableTiming));
   }
   size_t pending_at[kPipeStreams] = {}, pending_m[kPipeStreams] = {};
   auto drain = [&](int s) -> int {
     if (!pending_m[s]) return CUZK_OK;
-    CK(cudaEventSynchronize(g_pin[s].done));
-    g_copy_pool.copy(static_cast<char *>(host) + pending_at[s], g_pin[s].buf[0], pending_m[s]);
+    CK(cudaEventSynchronize(c.pin[s].done));
+    g_copy_pool.copy(static_cast<char *>(host) + pending_at[s], c.pin[s].buf[0], pending_m[s]);
     pending_m[s] = 0;
     return CUZK_OK;
   };
   size_t at = 0;
-  for (int c = 0; at < bytes; ++c) {
-    const int s = c % kPipeStreams;
+  for (int k = 0; at < bytes; ++k) {
+    const int s = k % kPipeStreams;
     const size_t m = std::min(kBulkPiece, bytes - at);
     if ((rc = drain(s))) return rc;
-    CK(cudaMemcpyAsync(g_pin[s].buf[0], static_cast<const char *>(dev) + at, m, cudaMemcpyDeviceToHost, st));
-    CK(cudaEventRecord(g_pin[s].done, st));
+    CK(cudaMemcpyAsync(c.pin[s].buf[0], static_cast<const char *>(dev) + at, m, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(c.pin[s].done, st));
     pending_at[s] = at;
     pending_m[s] = m;
     at += m;
@@ -274,14 +330,14 @@ int bulk_download(void *host, const void *dev, size_t bytes, cudaStream_t st) {
   return CUZK_OK;
 }
 
-// Chunked, double-buffered host->device->host pass.  `nin` input arrays of `in_bytes[k]` bytes per unit, one output
+// Chunked, multi-stream host->device->host pass.  `nin` input arrays of `in_bytes[k]` bytes per unit, one output
 // array of `out_bytes` per unit (out may alias in[0] for in-place ops).  launch(stream, d_in[], d_out, m) enqueues the
 // kernel(s) for m units.  Returns after every result byte is in `out`.
 template <class Launch>
-int host_pipeline(size_t n, size_t chunk, int nin, const void *const *in, const size_t *in_bytes, void *out, size_t out_bytes,
+int host_pipeline(Ctx &c, size_t n, size_t chunk, int nin, const void *const *in, const size_t *in_bytes, void *out, size_t out_bytes,
                   bool out_aliases_in0, Launch launch) {
-  std::lock_guard<std::mutex> lk(g_hp_mu);
-  int rc = hp_start();
+  std::lock_guard<std::mutex> lk(c.hp_mu);
+  int rc = hp_start(c);
   if (rc) return rc;
   if (const char *env = getenv("CUZK_CHUNK_PERCENT")) {   // tuning knob: chunk size in percent of the default
     const long pct = atol(env);
@@ -299,44 +355,44 @@ int host_pipeline(size_t n, size_t chunk, int nin, const void *const *in, const 
   }
   for (int s = 0; s < kPipeStreams; ++s) {
     for (int k = 0; k < nin; ++k)
-      if ((rc = hp_reserve(g_hp.buf[s][k], g_hp.cap[s][k], chunk * in_bytes[k]))) return rc;
-    if (!out_aliases_in0 && (rc = hp_reserve(g_hp.buf[s][kPipeSlots - 1], g_hp.cap[s][kPipeSlots - 1], chunk * out_bytes))) return rc;
+      if ((rc = hp_reserve(c.buf[s][k], c.cap[s][k], chunk * in_bytes[k]))) return rc;
+    if (!out_aliases_in0 && (rc = hp_reserve(c.buf[s][kPipeSlots - 1], c.cap[s][kPipeSlots - 1], chunk * out_bytes))) return rc;
     if (staged) {
       for (int k = 0; k < nin; ++k)
-        if ((rc = pin_reserve(g_pin[s].buf[k], g_pin[s].cap[k], chunk * in_bytes[k]))) return rc;
-      if ((rc = pin_reserve(g_pin[s].buf[kPipeSlots - 1], g_pin[s].cap[kPipeSlots - 1], chunk * out_bytes))) return rc;
-      if (!g_pin[s].done) CK(cudaEventCreateWithFlags(&g_pin[s].done, cudaEventDisableTiming));
+        if ((rc = pin_reserve(c.pin[s].buf[k], c.pin[s].cap[k], chunk * in_bytes[k]))) return rc;
+      if ((rc = pin_reserve(c.pin[s].buf[kPipeSlots - 1], c.pin[s].cap[kPipeSlots - 1], chunk * out_bytes))) return rc;
+      if (!c.pin[s].done) CK(cudaEventCreateWithFlags(&c.pin[s].done, cudaEventDisableTiming));
     }
   }
   size_t done = 0;
   size_t drain_at[kPipeStreams] = {}, drain_m[kPipeStreams] = {};   // staged mode: the chunk whose results sit in each bounce buffer
   auto drain = [&](int s) -> int {
     if (drain_m[s] == 0) return CUZK_OK;
-    CK(cudaEventSynchronize(g_pin[s].done));
-    g_copy_pool.copy(static_cast<char *>(out) + drain_at[s] * out_bytes, g_pin[s].buf[kPipeSlots - 1], drain_m[s] * out_bytes);
+    CK(cudaEventSynchronize(c.pin[s].done));
+    g_copy_pool.copy(static_cast<char *>(out) + drain_at[s] * out_bytes, c.pin[s].buf[kPipeSlots - 1], drain_m[s] * out_bytes);
     drain_m[s] = 0;
     return CUZK_OK;
   };
-  for (int c = 0; done < n; ++c) {
-    const int s = c % kPipeStreams;
+  for (int k2 = 0; done < n; ++k2) {
+    const int s = k2 % kPipeStreams;
     const size_t m = (n - done < chunk) ? n - done : chunk;
-    cudaStream_t st = g_hp.stream[s];
+    cudaStream_t st = c.stream[s];
     void *d_in[kPipeSlots] = {};
     if (staged && (rc = drain(s))) return rc;   // the slot's previous results leave before its buffers are reused
     for (int k = 0; k < nin; ++k) {
-      d_in[k] = g_hp.buf[s][k];
+      d_in[k] = c.buf[s][k];
       const char *src = static_cast<const char *>(in[k]) + done * in_bytes[k];
       if (staged) {
-        g_copy_pool.copy(g_pin[s].buf[k], src, m * in_bytes[k]);
-        src = static_cast<const char *>(g_pin[s].buf[k]);
+        g_copy_pool.copy(c.pin[s].buf[k], src, m * in_bytes[k]);
+        src = static_cast<const char *>(c.pin[s].buf[k]);
       }
       CK(cudaMemcpyAsync(d_in[k], src, m * in_bytes[k], cudaMemcpyHostToDevice, st));
     }
-    void *d_out = out_aliases_in0 ? d_in[0] : g_hp.buf[s][kPipeSlots - 1];
+    void *d_out = out_aliases_in0 ? d_in[0] : c.buf[s][kPipeSlots - 1];
     if ((rc = launch(st, d_in, d_out, m))) return rc;
     if (staged) {
-      CK(cudaMemcpyAsync(g_pin[s].buf[kPipeSlots - 1], d_out, m * out_bytes, cudaMemcpyDeviceToHost, st));
-      CK(cudaEventRecord(g_pin[s].done, st));
+      CK(cudaMemcpyAsync(c.pin[s].buf[kPipeSlots - 1], d_out, m * out_bytes, cudaMemcpyDeviceToHost, st));
+      CK(cudaEventRecord(c.pin[s].done, st));
       drain_at[s] = done;
       drain_m[s] = m;
     } else {
@@ -348,36 +404,40 @@ int host_pipeline(size_t n, size_t chunk, int nin, const void *const *in, const 
     for (int s = 0; s < kPipeStreams; ++s)
       if ((rc = drain(s))) return rc;
   }
-  for (int s = 0; s < kPipeStreams; ++s) CK(cudaStreamSynchronize(g_hp.stream[s]));
+  for (int s = 0; s < kPipeStreams; ++s) CK(cudaStreamSynchronize(c.stream[s]));
   return CUZK_OK;
 }
 
-// makes the padding constants E_0 .. E_{need-1} of `arity` available on the device.  The chain is sequential (one thread,
-// ceil(arity/2) permutations per level), so it is computed only as far as trees need it, extended on demand, and the
-// values -- constants of the hash function -- are cached on the host across cuzk_shutdown / cuzk_init cycles.
-int ensure_padding(unsigned arity, int need = 2) {
+// makes the padding constants E_0 .. E_{need-1} of `arity` available on the device.  The chain is sequential
+// (ceil(arity/2) permutations per level), so it is computed only as far as trees need it, extended on demand, and the
+// values -- constants of the hash function -- are cached on the host across cuzk_shutdown / cuzk_init cycles and devices.
+// Upload and chain run on the legacy stream and are complete before this returns (the blocking copies and an explicit
+// stream synchronisation), so consumers on any stream, blocking or not, see the constants.
+int ensure_padding(Ctx &c, unsigned arity, int need = 2) {
   if (need > kMaxPadLevels) return fail(CUZK_ERR_INVALID, "tree too tall");
-  std::lock_guard<std::mutex> lk(g_pad_mu);
-  if (g_d_pad[arity] && g_pad_levels[arity] >= need) return CUZK_OK;
-  if (!g_d_pad[arity]) {
+  std::lock_guard<std::mutex> lk(c.pad_mu);
+  if (c.d_pad[arity] && c.pad_levels[arity] >= need) return CUZK_OK;
+  if (!c.d_pad[arity]) {
     uint64_t *d = nullptr;
     CK(cudaMalloc(&d, (size_t)kMaxPadLevels * 32));
-    g_d_pad[arity] = d;
-    g_pad_levels[arity] = 0;
+    c.d_pad[arity] = d;
+    c.pad_levels[arity] = 0;
   }
-  uint64_t *d = g_d_pad[arity];
-  if (g_pad_levels[arity] < g_h_pad_levels[arity]) {   // bring the device copy up to what the host already knows
+  uint64_t *d = c.d_pad[arity];
+  std::lock_guard<std::mutex> host_lk(g_pad_mu);   // the host copy is shared by all devices
+  if (c.pad_levels[arity] < g_h_pad_levels[arity]) {   // bring the device copy up to what the host already knows
     CK(cudaMemcpy(d, g_h_pad[arity], (size_t)g_h_pad_levels[arity] * 32, cudaMemcpyHostToDevice));
-    g_pad_levels[arity] = g_h_pad_levels[arity];
+    CK(cudaStreamSynchronize(0));   // a pageable upload may return before the DMA has landed
+    c.pad_levels[arity] = g_h_pad_levels[arity];
   }
-  if (g_pad_levels[arity] >= need) return CUZK_OK;
-  const int start = g_pad_levels[arity], end = std::min(kMaxPadLevels, std::max(need, start + 4));
-  if (g_coop_max != 0) coop_padding_chain_kernel<<<1, 32>>>(reinterpret_cast<uint4 *>(d), (int)arity, start, end);
+  if (c.pad_levels[arity] >= need) return CUZK_OK;
+  const int start = c.pad_levels[arity], end = std::min(kMaxPadLevels, std::max(need, start + 4));
+  if (g_coop_max.load() != 0) coop_padding_chain_kernel<<<1, 32>>>(reinterpret_cast<uint4 *>(d), (int)arity, start, end);
   else padding_chain_kernel<<<1, 32>>>(reinterpret_cast<uint4 *>(d), (int)arity, start, end);
   int rc = check_launch("padding_chain_kernel");
   if (rc) return rc;
-  CK(cudaMemcpy(g_h_pad[arity][start], d + 4 * start, (size_t)(end - start) * 32, cudaMemcpyDeviceToHost));
-  g_pad_levels[arity] = g_h_pad_levels[arity] = end;
+  CK(cudaMemcpy(g_h_pad[arity][start], d + 4 * start, (size_t)(end - start) * 32, cudaMemcpyDeviceToHost));   // waits for the chain
+  c.pad_levels[arity] = g_h_pad_levels[arity] = end;
   return CUZK_OK;
 }
 
@@ -405,75 +465,129 @@ int fr_batch_dev(int op, const uint64_t *a, const uint64_t *b, uint64_t *out, si
   return check_launch("fr_batch_kernel");
 }
 
-// Fuse two levels into one launch (merkle_fused2_kernel), or run them as two launches?  Both do the same hashing and a
-// node hash is ~190 k instructions against 288 bytes, so the saved middle-level traffic is worth nothing; what differs is
-// the tail.  A fused thread hashes arity + 1 nodes back to back, so the last, partly filled wave of CTAs costs
-// (arity + 1) node times, while per-level launches quantise in single node times.  Measured on B200 (tools/fuse_probe.py,
-// profiles/r01_fuse_probe.json): per-level launches win at every shard size (2^23 leaves, arity 8: 31.8 ms against
-// 45.2 ms fused; 2^26: 214 ms against 237 ms), so they are the default; the fused kernel stays selectable and
-// parity-tested (cuzk_debug_set_fuse).
-int g_fuse_mode = 0;   // 0: one launch per level, 1: fuse pairs of levels (cuzk_debug_set_fuse)
-inline bool fuse_two_levels(size_t /*mid_nodes*/, size_t out_nodes, unsigned /*arity*/) { return g_fuse_mode != 0 && out_nodes != 0; }
-
+// one level for `ntrees` trees of identical shape: narrow launches go to the cooperative kernel
 int launch_level(const uint4 *in, uint4 *out, size_t in_real, size_t out_count, unsigned arity, const uint4 *pad_in, cudaStream_t st,
                  size_t ntrees = 1, size_t tree_stride = 0) {
+  if (out_count * ntrees == 0) return CUZK_OK;
   if (use_coop(out_count * ntrees)) {
-    coop_merkle_level_kernel<<<coop_grid(out_count * ntrees), kCoopBlock, 0, st>>>(in, out, in_real, out_count, (int)arity, pad_in, pad_in + 2,
-                                                                               ntrees, tree_stride);
+    coop_merkle_level_kernel<<<coop_grid(out_count * ntrees), kCoopBlock, 0, st>>>(in, out, in_real, out_count, (int)arity, pad_in,
+                                                                                  pad_in + 2, ntrees, tree_stride);
     return check_launch("coop_merkle_level_kernel");
   }
   merkle_level_kernel<<<grid_for(out_count * ntrees, kBlock), kBlock, 0, st>>>(in, out, in_real, out_count, (int)arity, pad_in, pad_in + 2,
                                                                                ntrees, tree_stride);
   return check_launch("merkle_level_kernel");
 }
-int launch_fused2(const uint4 *in, uint4 *mid, uint4 *out, size_t in_real, size_t out_count, unsigned arity, const uint4 *pad_in,
-                  cudaStream_t st, size_t ntrees = 1, size_t tree_stride = 0) {
-  const size_t smem = (size_t)2 * arity * kBlock * sizeof(uint4);
-  merkle_fused2_kernel<<<grid_for(out_count * ntrees, kBlock), kBlock, smem, st>>>(in, mid, out, in_real, out_count, (int)arity, pad_in,
-                                                                                   ntrees, tree_stride);
-  return check_launch("merkle_fused2_kernel");
+
+int subtree_streams_start(Ctx &c) {
+  if (c.sub_fork) return CUZK_OK;
+  for (int i = 0; i < kSubtreeStreams; ++i) {
+    CK(cudaStreamCreateWithFlags(&c.sub_stream[i], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c.sub_join[i], cudaEventDisableTiming));
+  }
+  CK(cudaEventCreateWithFlags(&c.sub_fork, cudaEventDisableTiming));
+  return CUZK_OK;
+}
+void subtree_streams_stop(Ctx &c) {
+  for (int i = 0; i < kSubtreeStreams; ++i) {
+    if (c.sub_stream[i]) cudaStreamDestroy(c.sub_stream[i]);
+    if (c.sub_join[i]) cudaEventDestroy(c.sub_join[i]);
+    c.sub_stream[i] = nullptr;
+    c.sub_join[i] = nullptr;
+  }
+  if (c.sub_fork) cudaEventDestroy(c.sub_fork);
+  c.sub_fork = nullptr;
 }
 
-// builds `ntrees` trees of n leaves each in one pass: one launch per level (or per two levels) for the whole forest.
+// builds `ntrees` trees of n leaves each: one launch per level for the whole forest (build_tree_bottom_up,
+// merkle_tree.cpp:66-97 / the per-level loop of merkle_tree_cuda.cu:188-192).  A single large tree is cut into groups of
+// subtrees that run their lower levels on separate internal streams, so the narrow upper levels of one group (each costs a
+// permutation latency however few nodes it has) hide behind the wide lower levels of the next; the levels above the cut run
+// on the caller's stream after the groups have joined.  Every level is stored.
 // leaves: ntrees x n elements; levels_out: ntrees flat level-major trees of total_nodes(n) elements each.
-int merkle_build_dev(const uint64_t *leaves, size_t n, unsigned arity, uint64_t *levels_out, cudaStream_t st, size_t ntrees = 1) {
-  int rc = ensure_padding(arity, (int)cuzk_merkle_num_levels(n, arity) + 1);
+// padded_override (0 = derive from n) forces the padded leaf count (a power of arity >= n): shards of a larger tree.
+// allow_groups = false keeps everything on `st` (callers that run several builds on the internal streams themselves).
+// pad_shift: the "leaves" are nodes of level pad_shift of a larger tree, so missing ones are the constant E_pad_shift.
+int merkle_build_dev(Ctx &c, const uint64_t *leaves, size_t n, unsigned arity, uint64_t *levels_out, cudaStream_t st, size_t ntrees = 1,
+                     size_t padded_override = 0, bool allow_groups = true, int pad_shift = 0) {
+  const size_t padded = padded_override ? padded_override : cuzk_merkle_padded_leaves(n, arity);
+  int nlv = 0;   // levels including the leaves
+  size_t stride = 0;
+  for (size_t p = padded;; p /= arity) {
+    stride += p;
+    ++nlv;
+    if (p == 1) break;
+  }
+  int rc = ensure_padding(c, arity, nlv + 1 + pad_shift);
   if (rc) return rc;
-  const uint4 *pad = reinterpret_cast<const uint4 *>(g_d_pad[arity]);
-  size_t padded = cuzk_merkle_padded_leaves(n, arity);
-  const size_t stride = cuzk_merkle_total_nodes(n, arity);
-  uint4 *cur = reinterpret_cast<uint4 *>(levels_out);
-  merkle_pad_leaves_kernel<<<grid_for(padded * ntrees, 256), 256, 0, st>>>(reinterpret_cast<const uint4 *>(leaves), n, padded, pad, cur,
+  const uint4 *pad = reinterpret_cast<const uint4 *>(c.d_pad[arity]) + 2 * pad_shift;
+  uint4 *base = reinterpret_cast<uint4 *>(levels_out);
+  merkle_pad_leaves_kernel<<<grid_for(padded * ntrees, 256), 256, 0, st>>>(reinterpret_cast<const uint4 *>(leaves), n, padded, pad, base,
                                                                           ntrees, stride);
   if ((rc = check_launch("merkle_pad_leaves_kernel"))) return rc;
-  size_t p = padded, real = n;
-  int level = 0;
-  while (p > 1) {
-    const size_t q = p / arity;
-    if (q > 1 && fuse_two_levels(q * ntrees, (q / arity) * ntrees, arity)) {
-      const size_t q2 = q / arity;
-      if ((rc = launch_fused2(cur, cur + 2 * p, cur + 2 * p + 2 * q, real, q2, arity, pad + 2 * level, st, ntrees, stride))) return rc;
-      cur += 2 * p + 2 * q;
-      real = ceil_div(ceil_div(real, arity), arity);
-      p = q2;
-      level += 2;
-    } else {
-      if ((rc = launch_level(cur, cur + 2 * p, real, q, arity, pad + 2 * level, st, ntrees, stride))) return rc;
-      cur += 2 * p;
-      real = ceil_div(real, arity);
-      p = q;
-      level += 1;
+
+  // the cut: the tallest subtrees of which the real leaves still fill at least kSubtreeStreams; only for trees large enough
+  // that their lower levels are throughput-bound (several waves) while their upper ones are latency-bound
+  size_t span = 1;
+  int cut = 0;   // levels [0, cut) are hashed group by group, the rest on the caller's stream
+  if (allow_groups && ntrees == 1 && c.sub_fork != nullptr && n >= ((size_t)1 << 17)) {
+    while (cut < nlv - 1 && ceil_div(n, span * arity) >= (size_t)kSubtreeStreams) {
+      span *= arity;
+      ++cut;
     }
+  }
+  const size_t real_subtrees = ceil_div(n, span);
+  const size_t groups = cut >= 2 ? std::min<size_t>(real_subtrees, kSubtreeStreams) : 1;
+  if (groups >= 2) {
+    std::lock_guard<std::mutex> lk(c.sub_mu);
+    CK(cudaEventRecord(c.sub_fork, st));
+    const size_t total_subtrees = padded / span;
+    for (size_t g = 0; g < groups; ++g) {
+      const size_t lo = real_subtrees * g / groups;
+      const size_t hi = (g + 1 == groups) ? total_subtrees : real_subtrees * (g + 1) / groups;   // the last group also writes the padding nodes
+      cudaStream_t sg = c.sub_stream[g];
+      CK(cudaStreamWaitEvent(sg, c.sub_fork, 0));
+      uint4 *cur = base;
+      size_t p = padded, first = lo * span, width = (hi - lo) * span;   // this group's nodes on the current level
+      size_t real = n > first ? std::min(n - first, width) : 0;
+      for (int level = 0; level < cut; ++level) {
+        if ((rc = launch_level(cur + 2 * first, cur + 2 * p + 2 * (first / arity), real, width / arity, arity, pad + 2 * level, sg))) return rc;
+        cur += 2 * p;
+        p /= arity;
+        first /= arity;
+        width /= arity;
+        real = ceil_div(real, arity);
+      }
+      CK(cudaEventRecord(c.sub_join[g], sg));
+      CK(cudaStreamWaitEvent(st, c.sub_join[g], 0));
+    }
+  } else {
+    cut = 0;
+  }
+  // the remaining levels, whole width, on the caller's stream
+  uint4 *cur = base;
+  size_t p = padded, real = n;
+  for (int level = 0; level < cut; ++level) {
+    cur += 2 * p;
+    p /= arity;
+    real = ceil_div(real, arity);
+  }
+  for (int level = cut; p > 1; ++level) {
+    const size_t q = p / arity;
+    if ((rc = launch_level(cur, cur + 2 * p, real, q, arity, pad + 2 * level, st, ntrees, stride))) return rc;
+    cur += 2 * p;
+    real = ceil_div(real, arity);
+    p = q;
   }
   return CUZK_OK;
 }
 
 // roots of `count` consecutive subtrees of arity^height (virtual) leaves whose first n leaves are in memory
-int subtree_roots_one_stream(const uint64_t *leaves, size_t n, unsigned arity, unsigned height, size_t count, uint64_t *roots_out,
+int subtree_roots_one_stream(Ctx &c, const uint64_t *leaves, size_t n, unsigned arity, unsigned height, size_t count, uint64_t *roots_out,
                              cudaStream_t st) {
-  int rc = ensure_padding(arity, (int)height + 2);
+  int rc = ensure_padding(c, arity, (int)height + 2);
   if (rc) return rc;
-  const uint4 *pad = reinterpret_cast<const uint4 *>(g_d_pad[arity]);
+  const uint4 *pad = reinterpret_cast<const uint4 *>(c.d_pad[arity]);
   if (height == 0) {
     merkle_pad_leaves_kernel<<<grid_for(count, 256), 256, 0, st>>>(reinterpret_cast<const uint4 *>(leaves), n, count, pad,
                                                                   reinterpret_cast<uint4 *>(roots_out), 1, 0);
@@ -487,14 +601,10 @@ int subtree_roots_one_stream(const uint64_t *leaves, size_t n, unsigned arity, u
   };
   const uint4 *cur = reinterpret_cast<const uint4 *>(leaves);
   size_t real = n;
-  unsigned level = 0;
   int flip = 0;
-  while (level < height) {
-    const unsigned step =
-        (height - level >= 2 && fuse_two_levels(ceil_div(real, arity), ceil_div(real, (size_t)arity * arity), arity)) ? 2 : 1;
-    const bool last = level + step == height;
-    size_t out_real = ceil_div(real, arity);
-    if (step == 2) out_real = ceil_div(out_real, arity);
+  for (unsigned level = 0; level < height; ++level) {
+    const bool last = level + 1 == height;
+    const size_t out_real = ceil_div(real, arity);
     const size_t out_count = last ? count : out_real;
     uint4 *dst;
     if (last) {
@@ -506,68 +616,39 @@ int subtree_roots_one_stream(const uint64_t *leaves, size_t n, unsigned arity, u
       dst = reinterpret_cast<uint4 *>(scratch[flip]);
       flip ^= 1;
     }
-    if (out_count) {
-      rc = (step == 2) ? launch_fused2(cur, nullptr, dst, real, out_count, arity, pad + 2 * level, st)
-                       : launch_level(cur, dst, real, out_count, arity, pad + 2 * level, st);
-      if (rc) { release(); return rc; }
-    }
+    rc = launch_level(cur, dst, real, out_count, arity, pad + 2 * level, st);
+    if (rc) { release(); return rc; }
     cur = dst;
     real = out_real;
-    level += step;
   }
   release();
   return CUZK_OK;
 }
 
 // The upper levels of a subtree are narrow: a level with fewer nodes than the chip has thread slots takes one node-hash
-// latency (about 0.18 ms per permutation) however few nodes it has.  With several subtrees per call, groups of subtrees run
-// on separate internal streams, so the narrow levels of one group hide behind the wide levels of the next.
-constexpr int kSubtreeStreams = 4;
-cudaStream_t g_sub_stream[kSubtreeStreams] = {};
-cudaEvent_t g_sub_fork = nullptr, g_sub_join[kSubtreeStreams] = {};
-std::mutex g_sub_mu;   // the internal streams and events are shared by all callers
-
-int subtree_streams_start() {
-  if (g_sub_fork) return CUZK_OK;
-  for (int i = 0; i < kSubtreeStreams; ++i) {
-    CK(cudaStreamCreateWithFlags(&g_sub_stream[i], cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&g_sub_join[i], cudaEventDisableTiming));
-  }
-  CK(cudaEventCreateWithFlags(&g_sub_fork, cudaEventDisableTiming));
-  return CUZK_OK;
-}
-void subtree_streams_stop() {
-  for (int i = 0; i < kSubtreeStreams; ++i) {
-    if (g_sub_stream[i]) cudaStreamDestroy(g_sub_stream[i]);
-    if (g_sub_join[i]) cudaEventDestroy(g_sub_join[i]);
-    g_sub_stream[i] = nullptr;
-    g_sub_join[i] = nullptr;
-  }
-  if (g_sub_fork) cudaEventDestroy(g_sub_fork);
-  g_sub_fork = nullptr;
-}
-
-int subtree_roots_dev(const uint64_t *leaves, size_t n, unsigned arity, unsigned height, size_t count, uint64_t *roots_out,
+// latency however few nodes it has.  With several subtrees per call, groups of subtrees run on separate internal streams,
+// so the narrow levels of one group hide behind the wide levels of the next.
+int subtree_roots_dev(Ctx &c, const uint64_t *leaves, size_t n, unsigned arity, unsigned height, size_t count, uint64_t *roots_out,
                       cudaStream_t st) {
   size_t span = 1;
   for (unsigned i = 0; i < height; ++i) span *= arity;
   const size_t real_subtrees = ceil_div(n, span);   // subtrees with at least one real leaf; the rest are padding constants
   const size_t groups = std::min<size_t>(real_subtrees, kSubtreeStreams);
-  if (height < 3 || groups < 2 || g_sub_fork == nullptr) return subtree_roots_one_stream(leaves, n, arity, height, count, roots_out, st);
-  std::lock_guard<std::mutex> lk(g_sub_mu);
-  CK(cudaEventRecord(g_sub_fork, st));
+  if (height < 3 || groups < 2 || c.sub_fork == nullptr) return subtree_roots_one_stream(c, leaves, n, arity, height, count, roots_out, st);
+  std::lock_guard<std::mutex> lk(c.sub_mu);
+  CK(cudaEventRecord(c.sub_fork, st));
   int rc = CUZK_OK;
   for (size_t g = 0; g < groups; ++g) {
     const size_t lo = real_subtrees * g / groups;
     const size_t hi = (g + 1 == groups) ? count : real_subtrees * (g + 1) / groups;   // the last group also writes the padding roots
     const size_t first_leaf = lo * span;
     const size_t n_g = std::min(n - first_leaf, (hi - lo) * span);
-    cudaStream_t sg = g_sub_stream[g];
-    CK(cudaStreamWaitEvent(sg, g_sub_fork, 0));
-    const int r = subtree_roots_one_stream(leaves + 4 * first_leaf, n_g, arity, height, hi - lo, roots_out + 4 * lo, sg);
+    cudaStream_t sg = c.sub_stream[g];
+    CK(cudaStreamWaitEvent(sg, c.sub_fork, 0));
+    const int r = subtree_roots_one_stream(c, leaves + 4 * first_leaf, n_g, arity, height, hi - lo, roots_out + 4 * lo, sg);
     if (r && !rc) rc = r;
-    CK(cudaEventRecord(g_sub_join[g], sg));
-    CK(cudaStreamWaitEvent(st, g_sub_join[g], 0));
+    CK(cudaEventRecord(c.sub_join[g], sg));
+    CK(cudaStreamWaitEvent(st, c.sub_join[g], 0));
   }
   return rc;
 }

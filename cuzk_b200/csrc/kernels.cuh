@@ -229,85 +229,38 @@ __global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) merkle_level_kernel(c
   store_fr(out + 2 * i, r);
 }
 
-// two fused levels: thread i hashes `arity` groups of `arity` inputs into its own shared-memory slots and then hashes
-// those into out[i]; the middle level never reaches HBM unless `mid_out` is given (full-tree builds keep every level).
-// Same padding rules as merkle_level_kernel (pad_in / pad_mid / pad_out are consecutive padding constants).
-__global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) merkle_fused2_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ mid_out,
-                                                                uint4 *__restrict__ out, size_t in_real, size_t out_count,
-                                                                int arity, const uint4 *__restrict__ pad, size_t ntrees,
-                                                                size_t tree_stride) {
-  extern __shared__ uint4 smem[];                    // [2 * arity][kBlock] uint4: slot-major, so a warp's accesses never conflict
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  fr_table_init();
-  if (t >= out_count * ntrees) return;
-  const size_t tree = t / out_count, i = t - tree * out_count;   // forest form, see merkle_level_kernel
-  in += 2 * tree * tree_stride;
-  out += 2 * tree * tree_stride;
-  if (mid_out) mid_out += 2 * tree * tree_stride;
-  const uint4 *pad_in = pad, *pad_mid = pad + 2, *pad_out = pad + 4;
-  const size_t span = (size_t)arity * arity;
-  if (i * span >= in_real) {
-    out[2 * i] = pad_out[0];
-    out[2 * i + 1] = pad_out[1];
-    if (mid_out) {
-      for (int g = 0; g < arity; ++g) {
-        mid_out[2 * (i * arity + g)] = pad_mid[0];
-        mid_out[2 * (i * arity + g) + 1] = pad_mid[1];
-      }
-    }
+// incremental update, step 0: write the new leaf values (level 0).  Entry s of the batch, sorted by leaf index (stable, so
+// equal indices keep their batch order): only the LAST entry of a run of equal indices writes -- the value a serial loop of
+// update_leaf calls would leave behind (merkle_tree.cpp:294-301).  Indices >= n are skipped and counted in *oob (the
+// reference throws std::out_of_range there, :296-298).  pos == nullptr: the batch is unsorted and holds a single entry.
+__global__ void merkle_write_leaves_kernel(uint4 *__restrict__ level0, const u64 *__restrict__ sorted_idx, const u32 *__restrict__ pos,
+                                           const uint4 *__restrict__ values, size_t count, size_t n, unsigned long long *oob) {
+  size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= count) return;
+  const u64 idx = sorted_idx[s];
+  if (s + 1 < count && sorted_idx[s + 1] == idx) return;
+  if (idx >= n) {
+    atomicAdd(oob, 1ull);
     return;
   }
-  uint4 *mine = smem + threadIdx.x;                  // slot s of this thread lives at mine[s * kBlock]
-#pragma unroll 1
-  for (int g = 0; g < arity; ++g) {
-    const size_t first = i * span + (size_t)g * arity;
-    uint4 lo, hi;
-    if (first >= in_real) {
-      lo = pad_mid[0];
-      hi = pad_mid[1];
-    } else {
-      u32 r[8];
-      sponge_n(r, 3u, arity, [&](u32(&x)[8], int j) {
-        const uint4 *src = (first + j < in_real) ? in + 2 * (first + j) : pad_in;
-        load_fr_plain(x, src);
-      });
-      lo = make_uint4(r[0], r[1], r[2], r[3]);
-      hi = make_uint4(r[4], r[5], r[6], r[7]);
-    }
-    mine[(2 * g) * kBlock] = lo;
-    mine[(2 * g + 1) * kBlock] = hi;
-    if (mid_out) {
-      mid_out[2 * (i * arity + g)] = lo;
-      mid_out[2 * (i * arity + g) + 1] = hi;
-    }
-  }
-  u32 r[8];
-  sponge_n(r, 3u, arity, [&](u32(&x)[8], int j) {
-    const uint4 a = mine[(2 * j) * kBlock], b = mine[(2 * j + 1) * kBlock];
-    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
-    x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
-  });
-  store_fr(out + 2 * i, r);
-}
-
-// incremental update, step 0: write the new leaf values (level 0)
-__global__ void merkle_write_leaves_kernel(uint4 *__restrict__ level0, const u64 *__restrict__ indices, const uint4 *__restrict__ values,
-                                           size_t count) {
-  size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  fr_table_init();
-  if (q >= count) return;
-  const u64 idx = indices[q];
+  const size_t q = pos ? pos[s] : s;
   level0[2 * idx] = values[2 * q];
   level0[2 * idx + 1] = values[2 * q + 1];
 }
-// incremental update, one level: thread q re-hashes the level-`shift_level` ancestor of leaf indices[q] from its children.
-// Updates that share an ancestor compute the same value and store it twice (benign).  in = level l-1, out = level l.
+__global__ void iota_u32_kernel(u32 *out, size_t count) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = (u32)i;
+}
+// incremental update, one level: thread q re-hashes the level-l ancestor of leaf indices[q] from its children.
+// Updates that share an ancestor compute the same value from the same children and store it twice (benign); indices >= n
+// are skipped.  in = level l-1, out = level l.
 __global__ void __launch_bounds__(kBlock, CUZK_MIN_BLOCKS) merkle_update_level_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out,
-                                                                      const u64 *__restrict__ indices, size_t count, u64 divisor,
+                                                                      const u64 *__restrict__ indices, size_t count, size_t n, u64 divisor,
                                                                       int arity) {
   size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   fr_table_init();
   if (q >= count) return;
+  if (indices[q] >= n) return;
   const size_t node = indices[q] / divisor;          // ancestor index at the output level (divisor = arity^l)
   const uint4 *kids = in + 2 * node * (size_t)arity;
   u32 r[8];

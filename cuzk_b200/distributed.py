@@ -2,6 +2,12 @@
 
 The reference is single-GPU (no NCCL, no streams); this layer is new.
 
+On GPUs the sharded tree lives in the LIBRARY (cuzk_mg_*, csrc/multi_gpu.cuh): every rank keeps all levels of its subtrees in
+HBM and serves proofs from them, the library itself issues the one NCCL all-gather of subtree roots, and this module is a
+thin caller (``native_sharded_tree``): torch.distributed only carries the 128-byte NCCL id at start-up.  The pure
+torch.distributed formulation below (``sharded_merkle_root`` with an injected ``ops`` backend) is kept because it runs under
+gloo on CPU with the oracle as hasher, which is how the sharding logic is tested without GPUs.
+
 * Batch hashing shards by contiguous slices -- no collective.
 * Merkle build: the padded tree is cut at level ``m`` into subtrees of ``arity**m`` leaves.  The subtrees that
   contain real leaves are dealt to the ranks in contiguous blocks, each rank reduces its block to subtree
@@ -144,3 +150,15 @@ def sharded_all_valid(local_results, group=None) -> bool:
     if dist is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(flags, op=dist.ReduceOp.MIN, group=group)
     return bool(flags[0].item() == 1 and flags[1].item() == -1)
+
+
+def native_sharded_tree(local_leaves, n: int, arity: int, mg=None, group=None):
+    """The n-leaf tree sharded over the ranks of ``group`` through the library (cuzk_mg_tree_build): ``local_leaves`` is this
+    rank's CUDA tensor of leaves (``mg.shard_leaves(n, arity, rank)``).  Returns (tree, mg); the tree serves proofs for this
+    rank's leaves from the levels it keeps and verifies against the root every rank computed.  Collective."""
+    from . import api
+
+    if mg is None:
+        mg = api.MultiGpu.from_torch_distributed(local_leaves.device.index, group=group)
+    torch.cuda.synchronize(local_leaves.device)   # the library works on its own stream: the leaves must be complete
+    return mg.build_tree([local_leaves], n=n, arity=arity), mg

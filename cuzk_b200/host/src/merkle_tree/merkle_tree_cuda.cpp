@@ -46,11 +46,51 @@ CudaNaryMerkleTree::CudaNaryMerkleTree(const std::vector<FieldElement> &leaves, 
   build_tree(leaves);
 }
 
+CudaNaryMerkleTree::CudaNaryMerkleTree(const std::vector<FieldElement> &leaves, const MerkleTreeConfig &config, int gpus)
+    : config_(config), leaf_count_(0), tree_height_(0), gpus_(gpus < 1 ? 1 : gpus) {
+  ensure_library();
+  build_tree(leaves);
+}
+
 CudaNaryMerkleTree::~CudaNaryMerkleTree() = default;
+
+// multi-GPU mode: one cuzk_mg_t per object family (created on first use), the tree sharded over its devices
+bool CudaNaryMerkleTree::build_sharded(const std::vector<FieldElement> &leaves) {
+  if (!mg_) {
+    cuzk_mg_t *mg = nullptr;
+    if (cuzk_mg_init_local(gpus_, nullptr, &mg) != CUZK_OK) {
+      std::cerr << "CudaNaryMerkleTree: multi-GPU initialisation failed: " << cuzk_last_error() << std::endl;
+      return false;
+    }
+    mg_ = std::shared_ptr<void>(mg, [](void *h) { cuzk_mg_free(static_cast<cuzk_mg_t *>(h)); });
+  }
+  cuzk_mg_tree_t *t = nullptr;
+  const uint64_t *whole[1] = {raw(leaves)};
+  if (cuzk_mg_tree_build(static_cast<cuzk_mg_t *>(mg_.get()), whole, leaves.size(), (unsigned)config_.arity, CUZK_MEM_HOST, &t) != CUZK_OK ||
+      cuzk_mg_tree_root(t, root_.limbs) != CUZK_OK) {
+    std::cerr << "CudaNaryMerkleTree::build_tree (sharded): " << cuzk_last_error() << std::endl;
+    if (t) cuzk_mg_tree_free(t);
+    return false;
+  }
+  mg_tree_ = std::shared_ptr<void>(t, [](void *h) { cuzk_mg_tree_free(static_cast<cuzk_mg_tree_t *>(h)); });
+  return true;
+}
+
+bool CudaNaryMerkleTree::device_flat_proofs(const uint64_t *idx, size_t q, uint64_t *siblings, uint32_t *positions, size_t &levels_out) const {
+  if (mg_tree_) {
+    const cuzk_mg_tree_t *t = static_cast<const cuzk_mg_tree_t *>(mg_tree_.get());
+    levels_out = cuzk_mg_tree_num_levels(t) - 1;
+    return !q || !levels_out || cuzk_mg_tree_prove_batch(t, idx, q, siblings, positions) == CUZK_OK;
+  }
+  const cuzk_tree_t *t = static_cast<const cuzk_tree_t *>(device_tree_.get());
+  levels_out = cuzk_tree_num_levels(t) - 1;
+  return !q || !levels_out || cuzk_tree_prove_batch(t, idx, q, siblings, positions, CUZK_MEM_HOST, nullptr) == CUZK_OK;
+}
 
 bool CudaNaryMerkleTree::build_tree(const std::vector<FieldElement> &leaves) {
   tree_levels_.clear();
   device_tree_.reset();
+  mg_tree_.reset();
   levels_on_host_ = true;
   if (leaves.empty()) {  // an empty input clears the tree (merkle_tree_cuda.cu:142-148)
     leaf_count_ = 0;
@@ -61,6 +101,18 @@ bool CudaNaryMerkleTree::build_tree(const std::vector<FieldElement> &leaves) {
   if (!ensure_library()) return false;
   const unsigned arity = (unsigned)config_.arity;
   const size_t n = leaves.size();
+  if (gpus_ > 1) {   // sharded over several GPUs: the levels stay on their devices, the host keeps the root
+    if (!build_sharded(leaves)) {
+      leaf_count_ = 0;
+      tree_height_ = 0;
+      leaves_.clear();
+      return false;
+    }
+    if (&leaves != &leaves_) leaves_ = leaves;
+    leaf_count_ = n;
+    tree_height_ = cuzk_merkle_tree_height(n, arity);
+    return true;
+  }
   cuzk_tree_t *handle = nullptr;
   if (cuzk_tree_build(raw(leaves), n, arity, CUZK_MEM_HOST, nullptr, &handle) != CUZK_OK ||
       cuzk_tree_root(handle, root_.limbs, CUZK_MEM_HOST, nullptr) != CUZK_OK) {
@@ -121,12 +173,14 @@ void CudaNaryMerkleTree::adopt_levels(const std::vector<FieldElement> &leaves, c
 
 // proofs gathered by the GPU from the levels in HBM (cuzk_tree_prove_batch) and unpacked into MerkleProof objects
 bool CudaNaryMerkleTree::proofs_from_device(const std::vector<size_t> &valid_leaves, std::vector<MerkleProof> &out) const {
-  const cuzk_tree_t *t = static_cast<const cuzk_tree_t *>(device_tree_.get());
-  const size_t arity = config_.arity, nlv = cuzk_tree_num_levels(t) - 1, q = valid_leaves.size(), per = arity - 1;
+  const size_t arity = config_.arity, q = valid_leaves.size(), per = arity - 1;
+  const size_t nlv = mg_tree_ ? cuzk_mg_tree_num_levels(static_cast<const cuzk_mg_tree_t *>(mg_tree_.get())) - 1
+                              : cuzk_tree_num_levels(static_cast<const cuzk_tree_t *>(device_tree_.get())) - 1;
   std::vector<uint64_t> idx(valid_leaves.begin(), valid_leaves.end());
   std::vector<FieldElement> sib(q * nlv * per);
   std::vector<uint32_t> pos(q * nlv);
-  if (nlv && cuzk_tree_prove_batch(t, idx.data(), q, raw(sib), pos.data(), CUZK_MEM_HOST, nullptr) != CUZK_OK) {
+  size_t levels_seen = 0;
+  if (!device_flat_proofs(idx.data(), q, raw(sib), pos.data(), levels_seen)) {
     std::cerr << "CudaNaryMerkleTree: device proof generation failed: " << cuzk_last_error() << std::endl;
     return false;
   }
@@ -149,6 +203,11 @@ bool CudaNaryMerkleTree::proofs_from_device(const std::vector<size_t> &valid_lea
 
 std::optional<MerkleProof> CudaNaryMerkleTree::generate_proof(size_t leaf_index) const {
   if (leaf_index >= leaf_count_ || !has_tree()) return std::nullopt;
+  if (mg_tree_) {   // sharded tree: always served by the GPU that owns the leaf
+    std::vector<MerkleProof> one;
+    if (proofs_from_device({leaf_index}, one) && !one.empty()) return std::move(one[0]);
+    return std::nullopt;
+  }
   // a few single proofs are served from the device tree; a caller that keeps asking gets the host copy (one download)
   if (!levels_on_host_ && device_proofs_served_ < 64) {
     std::vector<MerkleProof> one;
@@ -178,6 +237,14 @@ std::optional<MerkleProof> CudaNaryMerkleTree::generate_proof(size_t leaf_index)
 std::vector<MerkleProof> CudaNaryMerkleTree::generate_batch_proofs(const std::vector<size_t> &indices) const {
   std::vector<MerkleProof> proofs;
   if (!has_tree()) return proofs;
+  if (mg_tree_) {
+    std::vector<size_t> valid;
+    valid.reserve(indices.size());
+    for (size_t i : indices)
+      if (i < leaf_count_) valid.push_back(i);
+    if (!proofs_from_device(valid, proofs)) proofs.clear();
+    return proofs;
+  }
   if (!levels_on_host_) {
     // the batch is gathered on the GPU unless it is so large that downloading the tree once is cheaper
     std::vector<size_t> valid;
@@ -206,13 +273,13 @@ bool CudaNaryMerkleTree::generate_flat_proofs(const std::vector<size_t> &leaf_in
   out.arity = config_.arity;
   out.leaf_indices.assign(leaf_indices.begin(), leaf_indices.end());
   const size_t q = leaf_indices.size();
-  if (device_tree_) {
-    const cuzk_tree_t *t = static_cast<const cuzk_tree_t *>(device_tree_.get());
-    out.levels = cuzk_tree_num_levels(t) - 1;
+  if (device_tree_ || mg_tree_) {
+    out.levels = mg_tree_ ? cuzk_mg_tree_num_levels(static_cast<const cuzk_mg_tree_t *>(mg_tree_.get())) - 1
+                          : cuzk_tree_num_levels(static_cast<const cuzk_tree_t *>(device_tree_.get())) - 1;
     out.positions.resize(q * out.levels);
     out.siblings.resize(q * out.levels * (out.arity - 1));
-    if (q && out.levels &&
-        cuzk_tree_prove_batch(t, out.leaf_indices.data(), q, raw(out.siblings), out.positions.data(), CUZK_MEM_HOST, nullptr) != CUZK_OK) {
+    size_t levels_seen = 0;
+    if (!device_flat_proofs(out.leaf_indices.data(), q, raw(out.siblings), out.positions.data(), levels_seen)) {
       std::cerr << "CudaNaryMerkleTree::generate_flat_proofs: " << cuzk_last_error() << std::endl;
       return false;
     }
@@ -245,8 +312,12 @@ bool CudaNaryMerkleTree::verify_flat_proofs(const FlatProofBatch &batch, const s
   if (batch.size() == 0) return true;
   if (!ensure_library()) return false;
   const FieldElement root = get_root_hash();
-  if (cuzk_merkle_verify_batch(raw(leaf_values), raw(batch.siblings), batch.positions.data(), batch.levels, (unsigned)batch.arity, root.limbs,
-                               verdicts.data(), batch.size(), CUZK_MEM_HOST, nullptr) != CUZK_OK) {
+  const bool sharded = mg_tree_ && batch.levels + 1 == cuzk_mg_tree_num_levels(static_cast<const cuzk_mg_tree_t *>(mg_tree_.get()));
+  const int rc = sharded ? cuzk_mg_tree_verify_batch(static_cast<const cuzk_mg_tree_t *>(mg_tree_.get()), raw(leaf_values), raw(batch.siblings),
+                                                     batch.positions.data(), verdicts.data(), batch.size())
+                         : cuzk_merkle_verify_batch(raw(leaf_values), raw(batch.siblings), batch.positions.data(), batch.levels,
+                                                    (unsigned)batch.arity, root.limbs, verdicts.data(), batch.size(), CUZK_MEM_HOST, nullptr);
+  if (rc != CUZK_OK) {
     std::cerr << "CudaNaryMerkleTree::verify_flat_proofs: " << cuzk_last_error() << std::endl;
     return false;
   }
@@ -260,12 +331,16 @@ bool CudaNaryMerkleTree::verify_batch_proofs_each(const std::vector<MerkleProof>
   if (!ensure_library()) return false;
   const size_t arity = config_.arity, sib_per_level = arity - 1;
   const FieldElement root = get_root_hash();
-  const FieldElement filler = compute_empty_hash(arity);  // stands in for a missing sibling (merkle_tree_cuda.cu:312-315)
-  // Proofs of equal length go to the GPU as one level-uniform batch; a proof whose path and indices disagree in length
-  // is rejected outright (the reference would read past the end of `indices`).
+  // Proofs of equal length go to the GPU as one level-uniform batch.  Rejected outright (verdict 0), as the reference's CPU
+  // verify_proof does (merkle_tree.cpp:217-219, :228-230): path and indices of different length, or a level that does not
+  // carry exactly arity - 1 siblings.
   std::map<size_t, std::vector<size_t>> by_len;
-  for (size_t q = 0; q < proofs.size(); ++q)
-    if (proofs[q].path.size() == proofs[q].indices.size()) by_len[proofs[q].path.size()].push_back(q);
+  for (size_t q = 0; q < proofs.size(); ++q) {
+    const MerkleProof &p = proofs[q];
+    bool well_formed = p.path.size() == p.indices.size();
+    for (size_t l = 0; well_formed && l < p.path.size(); ++l) well_formed = p.path[l].size() == sib_per_level;
+    if (well_formed) by_len[p.path.size()].push_back(q);
+  }
   for (const auto &group : by_len) {
     const size_t L = group.first, m = group.second.size();
     // flat, level-uniform copies of the batch (the layout of cuzk_merkle_verify_batch); raw buffers: every slot is written
@@ -277,10 +352,7 @@ bool CudaNaryMerkleTree::verify_batch_proofs_each(const std::vector<MerkleProof>
       std::memcpy(leaves.get() + 4 * k, leaf_values[group.second[k]].limbs, 32);
       for (size_t l = 0; l < L; ++l) {
         pos[k * L + l] = p.indices[l] < arity ? (uint32_t)p.indices[l] : 0xFFFFFFFFu;
-        const size_t have = std::min(p.path[l].size(), sib_per_level);
-        uint64_t *dst = sib.get() + (k * L + l) * sib_per_level * 4;
-        if (have) std::memcpy(dst, p.path[l].data(), have * 32);
-        for (size_t s2 = have; s2 < sib_per_level; ++s2) std::memcpy(dst + 4 * s2, filler.limbs, 32);
+        std::memcpy(sib.get() + (k * L + l) * sib_per_level * 4, p.path[l].data(), sib_per_level * 32);
       }
     }
     std::vector<uint8_t> res(m);

@@ -44,6 +44,12 @@ public:
   // -- construction: the library is brought up on first use; a tree given leaves is built at once
   explicit CudaNaryMerkleTree(const MerkleTreeConfig &cfg = MerkleTreeConfig());
   explicit CudaNaryMerkleTree(const std::vector<FieldElement> &leaf_values, const MerkleTreeConfig &cfg = MerkleTreeConfig());
+  // extension (no reference counterpart; opt-in): the tree sharded over `gpus` GPUs of the box through cuzk_mg_*.  The leaves
+  // are cut into contiguous subtrees, one block per GPU; every GPU keeps ALL levels of its subtrees in HBM and serves proofs
+  // from them; only the 32-byte subtree roots cross NVLink, in one NCCL all-gather issued by the library; the top levels are
+  // hashed on every GPU.  Root, proofs and verdicts are those of the single-GPU tree.  get_tree_levels() stays empty: no
+  // single device (and not the host) holds the whole tree.  build_tree() on such an object shards again.
+  CudaNaryMerkleTree(const std::vector<FieldElement> &leaf_values, const MerkleTreeConfig &cfg, int gpus);
   ~CudaNaryMerkleTree();
   CudaNaryMerkleTree(CudaNaryMerkleTree &&) = default;
   CudaNaryMerkleTree &operator=(CudaNaryMerkleTree &&) = default;
@@ -76,6 +82,7 @@ public:
   size_t get_arity() const { return config_.arity; }
   size_t get_leaf_count() const { return leaf_count_; }
   size_t get_tree_height() const { return tree_height_; }
+  int get_gpu_count() const { return gpus_; }
   const std::vector<FieldElement> &get_leaves() const { return leaves_; }
   const std::vector<std::vector<FieldElement>> &get_tree_levels() const {
     fetch_levels();
@@ -105,6 +112,9 @@ private:
   // root; the host copy the reference class keeps (level 0 = padded leaves ... last = root) is downloaded the first time
   // a caller asks for levels or proofs.
   std::shared_ptr<void> device_tree_;
+  // multi-GPU mode (gpus_ > 1): the cuzk_mg_t handle and the sharded tree, shared by copies of this object
+  int gpus_ = 1;
+  std::shared_ptr<void> mg_, mg_tree_;
   FieldElement root_;
   mutable std::vector<std::vector<FieldElement>> tree_levels_;
   mutable bool levels_on_host_ = true;
@@ -113,6 +123,9 @@ private:
 
   void fetch_levels() const;
   bool proofs_from_device(const std::vector<size_t> &valid_leaves, std::vector<MerkleProof> &out) const;
+  bool build_sharded(const std::vector<FieldElement> &leaf_values);
+  // flat proofs of valid leaf indices from wherever the levels live in HBM (one device tree, or the shards)
+  bool device_flat_proofs(const uint64_t *idx, size_t q, uint64_t *siblings, uint32_t *positions, size_t &levels_out) const;
   bool has_tree() const { return leaf_count_ != 0; }
   FieldElement compute_empty_hash(size_t arity) const;
   void adopt_levels(const std::vector<FieldElement> &leaves, const FieldElement *flat_levels);

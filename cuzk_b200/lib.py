@@ -82,6 +82,7 @@ _SIGS = {
     "cuzk_init": (C.c_int, [C.c_int]),
     "cuzk_shutdown": (C.c_int, []),
     "cuzk_is_initialized": (C.c_int, []),
+    "cuzk_is_initialized_on": (C.c_int, [C.c_int]),
     "cuzk_device_count": (C.c_int, []),
     "cuzk_device_info": (C.c_int, [C.c_int, C.c_void_p]),
     "cuzk_last_error": (C.c_char_p, []),
@@ -112,6 +113,8 @@ _SIGS = {
     "cuzk_tree_num_levels": (C.c_size_t, [C.c_void_p]),
     "cuzk_tree_total_nodes": (C.c_size_t, [C.c_void_p]),
     "cuzk_tree_arity": (C.c_uint, [C.c_void_p]),
+    "cuzk_tree_device": (C.c_int, [C.c_void_p]),
+    "cuzk_tree_oob_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "cuzk_tree_device_levels": (C.c_void_p, [C.c_void_p]),
     "cuzk_tree_root": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "cuzk_tree_levels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
@@ -120,10 +123,28 @@ _SIGS = {
     "cuzk_tree_verify_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "cuzk_tree_update_leaves": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "cuzk_tree_append_leaves": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "cuzk_mg_unique_id": (C.c_int, [C.c_void_p]),
+    "cuzk_mg_init_local": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "cuzk_mg_init_rank": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "cuzk_mg_free": (C.c_int, [C.c_void_p]),
+    "cuzk_mg_world": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "cuzk_mg_device": (C.c_int, [C.c_void_p, C.c_int]),
+    "cuzk_mg_stream": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "cuzk_mg_nccl_version": (C.c_int, []),
+    "cuzk_mg_shard_leaves": (C.c_int, [C.c_size_t, C.c_uint, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "cuzk_mg_tree_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_int, C.POINTER(C.c_void_p)]),
+    "cuzk_mg_tree_free": (C.c_int, [C.c_void_p]),
+    "cuzk_mg_tree_root": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cuzk_mg_tree_num_levels": (C.c_size_t, [C.c_void_p]),
+    "cuzk_mg_tree_leaf_count": (C.c_size_t, [C.c_void_p]),
+    "cuzk_mg_tree_subtree_height": (C.c_size_t, [C.c_void_p]),
+    "cuzk_mg_tree_shard_levels": (C.c_void_p, [C.c_void_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "cuzk_mg_tree_prove_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "cuzk_mg_tree_verify_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "cuzk_mg_poseidon_hash_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "cuzk_synth_elements": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]),
     "cuzk_synth_u64_leaves": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_void_p]),
     "cuzk_debug_fallback_count": (C.c_uint64, []),
-    "cuzk_debug_set_fuse": (C.c_int, [C.c_int]),
     "cuzk_debug_fast_ops": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "cuzk_debug_mds_layer": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "cuzk_imad_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),

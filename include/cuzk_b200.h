@@ -14,6 +14,13 @@
  *   - `mem`: CUZK_MEM_DEVICE = every pointer is device memory on the current CUDA device and the
  *     call is asynchronous on `stream`; CUZK_MEM_HOST = every pointer is host memory, the library
  *     stages through its own device buffers and returns after the results are in the host buffer.
+ *   - Devices: a process may initialise several devices (cuzk_init(d) for each); all library state
+ *     (constants, padding roots, staging buffers, internal streams) is kept per device.  Every entry
+ *     point runs on the CALLING THREAD'S CURRENT CUDA device, which must be an initialised one.  One
+ *     convenience: a thread whose current device was never initialised while exactly one other device
+ *     was (worker threads of a single-GPU program that never call cudaSetDevice) is switched to that
+ *     device for the duration of the call.  Tree handles and cuzk_mg_* handles remember their devices
+ *     and run there whatever the caller's current device is.
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
  *   - Return value: CUZK_OK (0) or a negative error code; cuzk_last_error() gives a message
  *     (thread-local).  Nothing throws, nothing calls exit, there is NO CPU fallback: without a
@@ -50,9 +57,10 @@ extern "C" {
 /* ---- lifecycle: CudaFieldArithmetic::initialize/cleanup (field_arithmetic_cuda.cuh:28-31),
  *      CudaPoseidonHash ctor/dtor (poseidon_cuda.cuh:26-27), CudaNaryMerkleTree::initialize_cuda/cleanup_cuda
  *      (merkle_tree_cuda.cuh:101-102).  Reference-counted and idempotent; never resets the device. ---- */
-int cuzk_init(int device);
-int cuzk_shutdown(void);
-int cuzk_is_initialized(void);
+int cuzk_init(int device);      /* also makes `device` the calling thread's current device, like the reference's cudaSetDevice(0) */
+int cuzk_shutdown(void);        /* releases the calling thread's current device (or the only initialised one) */
+int cuzk_is_initialized(void);  /* on any device */
+int cuzk_is_initialized_on(int device);
 int cuzk_device_count(void); /* CudaFieldArithmetic::get_device_count (field_arithmetic_cuda.cuh:60) */
 /* device properties for CudaFieldArithmetic::print_device_info (field_arithmetic_cuda.cu:633-645) and
  * CudaMerkleUtils::check_cuda_compatibility (merkle_tree_cuda.cu:596-616), so host code needs no CUDA runtime */
@@ -163,6 +171,7 @@ size_t cuzk_tree_leaf_count(const cuzk_tree_t *tree);
 size_t cuzk_tree_num_levels(const cuzk_tree_t *tree);
 size_t cuzk_tree_total_nodes(const cuzk_tree_t *tree);
 unsigned cuzk_tree_arity(const cuzk_tree_t *tree);
+int cuzk_tree_device(const cuzk_tree_t *tree);
 /* device pointer to the level-major node array (valid until cuzk_tree_free) */
 const uint64_t *cuzk_tree_device_levels(const cuzk_tree_t *tree);
 /* get_root_hash (merkle_tree_cuda.cuh:84): copies the 32-byte root to host or device memory */
@@ -177,16 +186,66 @@ int cuzk_tree_prove_batch(const cuzk_tree_t *tree, const uint64_t *indices, size
 int cuzk_tree_verify_batch(const cuzk_tree_t *tree, const uint64_t *leaf_values, const uint64_t *siblings,
                            const uint32_t *positions, uint8_t *results_out, size_t num_proofs, int mem, void *stream);
 /* NaryMerkleTree::update_leaf (merkle_tree.cpp:294-301; the reference rebuilds the whole tree per update) for a batch:
- * writes values[q] at leaf indices[q] (< leaf_count, distinct) and re-hashes only the ancestors, one launch per level:
- * count x (levels-1) x ceil(arity/2) permutations instead of a full rebuild. */
+ * writes values[q] at leaf indices[q] and re-hashes only the ancestors, one launch per level: count x (levels-1) x
+ * ceil(arity/2) permutations instead of a full rebuild.  The tree afterwards equals a serial loop of update_leaf calls in
+ * batch order: when an index occurs more than once its LAST value wins.  An index >= leaf_count (the reference throws
+ * std::out_of_range, :296-298): host-buffer calls are refused as a whole with CUZK_ERR_INVALID and write nothing;
+ * device-pointer calls are asynchronous, so they skip such entries and count them in cuzk_tree_oob_count. */
 int cuzk_tree_update_leaves(cuzk_tree_t *tree, const uint64_t *indices, const uint64_t *values, size_t count, int mem,
                             void *stream);
+/* how many out-of-range indices device-pointer updates have skipped since the tree was built (a blocking read) */
+int cuzk_tree_oob_count(const cuzk_tree_t *tree, uint64_t *count_out);
 
 /* NaryMerkleTree::insert_leaf (merkle_tree.cpp:290-293; a full rebuild per leaf in the reference) for a batch: appends
  * values[0..count) after the last leaf.  While the padded leaf level has room only the new leaves' ancestors are re-hashed;
  * when it overflows, the larger tree is rebuilt on the device from the leaves already there.  Either way the tree equals a
  * fresh build over all leaves. */
 int cuzk_tree_append_leaves(cuzk_tree_t *tree, const uint64_t *values, size_t count, int mem, void *stream);
+
+/* ---- several GPUs of one box (SURVEY.md section 8e / 8b "cuzk_mg_*"; no reference counterpart: the reference is single-GPU,
+ * field_arithmetic_cuda.cu:20).  Leaves shard into contiguous subtrees, one block of subtrees per GPU; every GPU keeps ALL levels
+ * of its subtrees in HBM and serves proofs from them; only the 32-byte subtree roots cross NVLink, in ONE NCCL all-gather issued
+ * by the library, and every GPU hashes the few top levels itself.  Batch hashing / verification: contiguous slices, no
+ * collective.  NCCL (libnccl.so.2) is loaded at the first cuzk_mg_init_* call, never at library load.
+ *   cuzk_mg_init_local : ONE process drives `ngpus` devices (devices == NULL: 0..ngpus-1); every call below then spans them.
+ *   cuzk_mg_init_rank  : one process PER GPU (torchrun / MPI): rank 0 calls cuzk_mg_unique_id, the host program carries the
+ *                        128 bytes to the other ranks, every rank calls cuzk_mg_init_rank; tree builds are then collective. ---- */
+typedef struct cuzk_mg cuzk_mg_t;
+typedef struct cuzk_mg_tree cuzk_mg_tree_t;
+int cuzk_mg_unique_id(uint8_t id_out[128]);
+int cuzk_mg_init_local(int ngpus, const int *devices, cuzk_mg_t **mg_out);
+int cuzk_mg_init_rank(int rank, int nranks, int device, const uint8_t id[128], cuzk_mg_t **mg_out);
+int cuzk_mg_free(cuzk_mg_t *mg);
+int cuzk_mg_world(const cuzk_mg_t *mg, int *nranks_out, int *nlocal_out, int *first_rank_out);
+int cuzk_mg_device(const cuzk_mg_t *mg, int local);     /* CUDA device of local shard `local` */
+void *cuzk_mg_stream(const cuzk_mg_t *mg, int local);   /* the cudaStream_t the handle's work on that device is ordered on */
+int cuzk_mg_nccl_version(void);                         /* of the NCCL that was loaded; 0 = none */
+/* which leaves rank `rank` of `nranks` holds in a sharded tree over n leaves: [first, first + count) (count may be 0) */
+int cuzk_mg_shard_leaves(size_t n, unsigned arity, int nranks, int rank, size_t *first_out, size_t *count_out);
+/* CudaNaryMerkleTree::build_tree (merkle_tree_cuda.cuh:56) over every GPU of the handle.  mem == CUZK_MEM_DEVICE:
+ * local_leaves[r] = the leaves of local shard r (cuzk_mg_shard_leaves of rank first_rank + r) in that device's memory;
+ * mem == CUZK_MEM_HOST: local_leaves[0] = the WHOLE leaf array in host memory, each shard uploads its own slice.
+ * Returns with the root known on the host.  Collective in one-process-per-GPU mode. */
+int cuzk_mg_tree_build(cuzk_mg_t *mg, const uint64_t *const *local_leaves, size_t n, unsigned arity, int mem,
+                       cuzk_mg_tree_t **tree_out);
+int cuzk_mg_tree_free(cuzk_mg_tree_t *tree);
+int cuzk_mg_tree_root(const cuzk_mg_tree_t *tree, uint64_t root_out[4]);
+size_t cuzk_mg_tree_num_levels(const cuzk_mg_tree_t *tree);      /* of the whole tree, leaves and root included */
+size_t cuzk_mg_tree_leaf_count(const cuzk_mg_tree_t *tree);
+size_t cuzk_mg_tree_subtree_height(const cuzk_mg_tree_t *tree);  /* hash levels kept per shard subtree */
+/* device pointer to local shard `local`'s levels: num_subtrees trees of nodes_per_subtree elements, each level-major */
+const uint64_t *cuzk_mg_tree_shard_levels(const cuzk_mg_tree_t *tree, int local, size_t *first_subtree_out,
+                                          size_t *num_subtrees_out, size_t *nodes_per_subtree_out);
+/* generate_batch_proofs (merkle_tree_cuda.cuh:74): host memory in and out, the wire format of cuzk_merkle_prove_batch over the
+ * levels of the WHOLE tree; every query is routed to the local shard that owns the leaf and served from the levels it keeps.
+ * Leaves owned by another process's shard (one-process-per-GPU mode) and indices >= n: position 0xFFFFFFFF on every level. */
+int cuzk_mg_tree_prove_batch(const cuzk_mg_tree_t *tree, const uint64_t *indices, size_t num_proofs, uint64_t *siblings_out,
+                             uint32_t *positions_out);
+/* verify_batch_proofs (merkle_tree_cuda.cuh:76) against the sharded tree's root: host memory, slices over the local devices */
+int cuzk_mg_tree_verify_batch(const cuzk_mg_tree_t *tree, const uint64_t *leaf_values, const uint64_t *siblings,
+                              const uint32_t *positions, uint8_t *results_out, size_t num_proofs);
+/* batch_hash_pairs over the local devices: host memory, contiguous slices, one host thread per device */
+int cuzk_mg_poseidon_hash_pairs(const cuzk_mg_t *mg, const uint64_t *left, const uint64_t *right, uint64_t *out, size_t n);
 
 /* ---- synthetic inputs: generated on the device so multi-GiB leaf sets need no upload.
  * element i, limb j = splitmix64(seed, 4*(start+i)+j), top limb masked to 60 bits when canonical != 0;
@@ -197,11 +256,6 @@ int cuzk_synth_u64_leaves(uint64_t *out, size_t n, uint64_t seed, uint64_t start
 /* test hook (device pointers): applies ONE MDS layer (apply_mds_matrix, poseidon.cpp:148-167) in place to n
  * canonical 3-element states; mode 0 = the production fast path with its exact fallback, 1 = exact path only */
 int cuzk_debug_mds_layer(uint64_t *states, size_t n, int mode, void *stream);
-
-/* Merkle builds run one launch per level by default (measured faster on B200, see csrc/cuzk_kernels.cu); mode 1 makes them
- * fuse pairs of levels into one launch (merkle_fused2_kernel, middle level through shared memory), mode 0 restores the
- * default.  Returns the previous mode.  Results are identical in both modes. */
-int cuzk_debug_set_fuse(int mode);
 
 /* Launches of at most `units` units (hashes, nodes, proofs, states) run on the cooperative kernels -- sixteen lanes per
  * permutation (csrc/coop.cuh), a fraction of the one-thread kernels' latency while the chip is not full -- larger ones on

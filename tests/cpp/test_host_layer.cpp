@@ -8,6 +8,7 @@
 #include <thread>
 #include <vector>
 
+#include "cuzk_b200.h"
 #include "../../cuzk_b200/host/src/merkle_tree/merkle_tree_cuda.cuh"
 #include "../../cuzk_b200/host/src/poseidon/cuda/poseidon_cuda.cuh"
 #include "../../cuzk_b200/host/src/poseidon/cuda/poseidon_cuda_benchmarks.hpp"
@@ -421,6 +422,57 @@ TEST_F(HostMerkle, ProofsVerifyAndCorruptionIsCaught) {
     ASSERT_TRUE(tree.verify_flat_proofs(flat, tampered, verdicts));
     for (size_t i = 0; i < n; ++i) EXPECT_EQ(verdicts[i], i == 5 ? 0 : 1);
     EXPECT_FALSE(tree.generate_flat_proofs({n}, flat));
+  }
+}
+
+TEST_F(HostMerkle, MalformedSiblingListsAreRejectedLikeTheCpuVerifier) {
+  // NaryMerkleTree::verify_proof (merkle_tree.cpp:228-230) rejects a level that does not carry exactly arity - 1 siblings:
+  // neither junk appended to a valid level nor a trailing sibling that happens to be padding may be dropped or filled in
+  const size_t arity = 4, n = 13;   // 13 leaves of 16: the last group of level 0 ends in padding
+  const auto leaves = u64_leaves(n, 99);
+  CudaNaryMerkleTree tree(leaves, MerkleTreeConfig(arity));
+  auto proofs = tree.generate_batch_proofs({0, 12, 5});
+  ASSERT_EQ(proofs.size(), 3u);
+  std::vector<FieldElement> vals{leaves[0], leaves[12], leaves[5]};
+  ASSERT_TRUE(tree.verify_batch_proofs(proofs, vals));
+  proofs[0].path[0].push_back(FieldElement(7));   // extra junk sibling
+  proofs[1].path[0].pop_back();                   // missing trailing sibling (a padding constant)
+  std::vector<uint8_t> res;
+  ASSERT_TRUE(tree.verify_batch_proofs_each(proofs, vals, res));
+  EXPECT_EQ(res, (std::vector<uint8_t>{0, 0, 1}));
+}
+
+TEST_F(HostMerkle, ShardedOverSeveralGpusEqualsTheSingleGpuTree) {
+  // opt-in multi-GPU constructor (cuzk_mg_*): with one GPU in the box it still exercises the sharded code path (one shard)
+  const int gpus = std::min(cuzk_device_count(), 8);
+  for (size_t arity : {2, 8}) {
+    const size_t n = arity == 2 ? 3000 : 40000;
+    const auto leaves = u64_leaves(n, 4242);
+    CudaNaryMerkleTree single(leaves, MerkleTreeConfig(arity));
+    CudaNaryMerkleTree sharded(leaves, MerkleTreeConfig(arity), gpus);
+    EXPECT_EQ(sharded.get_gpu_count(), std::max(gpus, 1));
+    ASSERT_EQ(sharded.get_leaf_count(), n);
+    EXPECT_EQ(sharded.get_root_hash(), single.get_root_hash());
+    std::vector<size_t> idx;
+    for (size_t i = 0; i < n; i += 37) idx.push_back(i);
+    idx.push_back(n - 1);
+    const auto a = single.generate_batch_proofs(idx), b = sharded.generate_batch_proofs(idx);
+    ASSERT_EQ(a.size(), b.size());
+    size_t differ = 0;
+    std::vector<FieldElement> vals;
+    for (size_t q = 0; q < a.size(); ++q) {
+      differ += a[q].path != b[q].path || a[q].indices != b[q].indices;
+      vals.push_back(leaves[idx[q]]);
+    }
+    EXPECT_EQ(differ, 0u);
+    EXPECT_TRUE(sharded.verify_batch_proofs(b, vals));
+    FlatProofBatch flat;
+    ASSERT_TRUE(sharded.generate_flat_proofs(idx, flat));
+    std::vector<uint8_t> verdicts;
+    vals[1] = FieldElement(vals[1].limbs[0] ^ 2);
+    ASSERT_TRUE(sharded.verify_flat_proofs(flat, vals, verdicts));
+    EXPECT_EQ(verdicts[0], 1);
+    EXPECT_EQ(verdicts[1], 0);
   }
 }
 

@@ -10,6 +10,20 @@ from test_oracle import mt19937_64_leaves
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=["default", "cooperative"])
+def kernel_path(request):
+    """Every test of this module runs twice: with the launchers' own choice between the one-thread-per-unit and the
+    cooperative (sixteen lanes per permutation) kernels, and with every launch of up to 2^20 units forced onto the
+    cooperative kernels.  Results must not depend on the path."""
+    from cuzk_b200 import lib
+
+    L = lib.get_lib()
+    old = L.cuzk_debug_set_coop_max(1 << 20) if request.param == "cooperative" else None
+    yield request.param
+    if old is not None:
+        L.cuzk_debug_set_coop_max(old)
+
 EDGE = ints_to_array([0, 1, 2, P_INT - 1, P_INT, P_INT + 1, 2 * P_INT, 5 * P_INT, 5 * P_INT + 1, 2**256 - 1, 2**128 - 1, 2**255, K_INT,
                       2**256 - 2**64, 2**64 - 1, (1 << 192) + (5 << 64), 1 + ((2**64 - 1) << 64), 2**224 - 1])
 
@@ -412,7 +426,7 @@ def test_config4_octary_2p26_sharded_equals_full_build(gpu, oracle):
         assert (to_host(out)[0] == root).all(), world
 
 
-def test_exact_fallback_path_is_bit_exact(gpu, oracle):
+def test_exact_fallback_path_is_bit_exact(gpu, oracle, kernel_path):
     """The production kernels evaluate every unit on a fast path whose top-word comparisons can be undecided (2^-32 each);
     such units are recomputed on the exact path.  libcuzk_b200_widen.so is the same source built with the flags widened
     to near misses, so a large share of the units takes the fallback: every result must still equal the oracle."""
@@ -426,6 +440,8 @@ def test_exact_fallback_path_is_bit_exact(gpu, oracle):
     assert os.path.exists(path), "libcuzk_b200_widen.so missing: run __graft_entry__.build()"
     D = lib.Lib(path)
     D.check(D.cuzk_init(0), "init(widen)")
+    if kernel_path == "cooperative":   # the widened flags of the cooperative kernels: every launch below goes through them
+        D.cuzk_debug_set_coop_max(1 << 20)
     try:
         before = D.cuzk_debug_fallback_count()
         n = 20_000
@@ -506,31 +522,158 @@ def test_device_tree_handle_and_incremental_update(gpu, oracle, arity):
         t.close()
 
 
-@pytest.mark.parametrize("mode", [0, 1])
-def test_fused_and_per_level_builds_agree_with_oracle(gpu, oracle, mode):
-    """merkle_fused2_kernel (two levels per launch, middle level through shared memory) and merkle_level_kernel give the
-    oracle's levels and subtree roots for every arity, including ragged and single-group trees."""
+@pytest.mark.parametrize("coop_max", [0, 64, 1 << 30])
+def test_builds_agree_with_oracle_whatever_the_kernel_mix(gpu, oracle, coop_max):
+    """Levels and subtree roots equal the oracle's for every arity, including ragged and single-group trees, whether the
+    levels run on the one-thread kernels only (0), switch to the cooperative kernels for levels of <= 64 nodes, or run on
+    the cooperative kernels throughout."""
     import torch
 
     from cuzk_b200 import lib
 
     L = lib.get_lib()
-    old = L.cuzk_debug_set_fuse(mode)
+    old = L.cuzk_debug_set_coop_max(coop_max)
     try:
-        rng = np.random.default_rng(mode)
+        rng = np.random.default_rng(coop_max % 7)
         for arity in range(2, 9):
             for n in (arity, arity * arity, arity**3 - 1, arity**3 + 1, 700):
                 leaves = rnd(rng, n, n % 2 == 0)
                 want = oracle.merkle_build(leaves, arity)
                 t = gpu.CudaNaryMerkleTree(to_dev(leaves), arity=arity)
                 got = [to_host(x) for x in t.get_tree_levels()]
-                assert len(got) == len(want) and all((g == w).all() for g, w in zip(got, want)), (mode, arity, n)
+                assert len(got) == len(want) and all((g == w).all() for g, w in zip(got, want)), (coop_max, arity, n)
                 # roots only (no middle level stored), whole tree as one subtree
                 root = torch.empty((1, 4), dtype=torch.int64, device="cuda")
                 L.check(L.cuzk_merkle_subtree_roots(to_dev(leaves).data_ptr(), n, arity, len(want) - 1, 1, root.data_ptr(), 0, None), "roots")
-                assert (to_host(root)[0] == want[-1][0]).all(), (mode, arity, n)
+                assert (to_host(root)[0] == want[-1][0]).all(), (coop_max, arity, n)
     finally:
-        L.cuzk_debug_set_fuse(old)
+        L.cuzk_debug_set_coop_max(old)
+
+
+def test_large_tree_built_in_groups_equals_oracle(gpu, oracle):
+    """Trees of >= 2^17 leaves hash their lower levels as groups of subtrees on internal streams (the narrow upper levels of
+    one group hide behind the wide levels of the next): every stored level must still equal the oracle's, full and ragged."""
+    for arity, n in ((2, (1 << 17) + 12345), (4, 1 << 18), (8, 300_000)):
+        leaves = synth_u64_leaves(40 + arity, n)
+        want = oracle.merkle_build(leaves, arity)
+        t = gpu.DeviceMerkleTree(to_dev(leaves), arity=arity)
+        got = t.get_tree_levels()
+        assert len(got) == len(want) and all((g == w).all() for g, w in zip(got, want)), (arity, n)
+        t.close()
+
+
+def test_update_semantics_duplicates_and_out_of_range(gpu, oracle):
+    """cuzk_tree_update_leaves equals a serial loop of update_leaf calls (merkle_tree.cpp:294-301): the LAST value of a repeated
+    index wins; an index >= leaf_count is refused on the host path (the reference throws) and skipped + counted on the
+    asynchronous device path, without touching memory outside the leaf level."""
+    import ctypes as C
+
+    import torch
+
+    from cuzk_b200 import lib
+
+    L = lib.get_lib()
+    rng = np.random.default_rng(77)
+    n, arity = 1000, 4
+    leaves = rnd(rng, n, True)
+    t = gpu.DeviceMerkleTree(to_dev(leaves), arity=arity)
+    idx = np.array([5, 17, 5, 999, 17, 5, 400], dtype=np.uint64)
+    vals = rnd(rng, idx.size, True)
+    expect = leaves.copy()
+    for i, v in zip(idx, vals):
+        expect[int(i)] = v
+    for where in ("device", "host"):
+        t2 = gpu.DeviceMerkleTree(to_dev(leaves), arity=arity)
+        if where == "device":
+            t2.update_leaves(torch.from_numpy(idx.view(np.int64)).cuda(), to_dev(vals))
+        else:
+            t2.update_leaves(idx, vals)
+        got, want = t2.get_tree_levels(), oracle.merkle_build(expect, arity)
+        assert all((g == w).all() for g, w in zip(got, want)), where
+        t2.close()
+    # out of range on the device path: skipped, counted, everything else applied
+    bad_idx = np.array([3, n, 2**40, 7, n + 5], dtype=np.uint64)
+    bad_vals = rnd(rng, bad_idx.size, True)
+    t.update_leaves(torch.from_numpy(bad_idx.view(np.int64)).cuda(), to_dev(bad_vals))
+    cnt = C.c_uint64()
+    L.check(L.cuzk_tree_oob_count(t._h, C.byref(cnt)), "oob")
+    assert cnt.value == 3
+    expect2 = leaves.copy()
+    expect2[3], expect2[7] = bad_vals[0], bad_vals[3]
+    assert all((g == w).all() for g, w in zip(t.get_tree_levels(), oracle.merkle_build(expect2, arity)))
+    with pytest.raises(Exception):
+        t.update_leaves(bad_idx, bad_vals)   # host path: refused as a whole
+    assert all((g == w).all() for g, w in zip(t.get_tree_levels(), oracle.merkle_build(expect2, arity)))
+    t.close()
+
+
+@pytest.mark.parametrize("arity,n", [(2, 5000), (8, 70_000), (4, 1), (3, 2)])
+def test_sharded_tree_handle_on_one_device(gpu, oracle, arity, n):
+    """cuzk_mg_* with a single shard (no NCCL involved): root, every proof path and the verdicts equal the oracle's for the
+    whole tree; out-of-range queries get the sentinel."""
+    leaves = synth_u64_leaves(60 + arity, n)
+    want = oracle.merkle_build(leaves, arity)
+    mg = gpu.MultiGpu.local(1)
+    try:
+        t = mg.build_tree(leaves, arity=arity)
+        assert (t.get_root_hash() == want[-1][0]).all()
+        assert t.num_levels == len(want)
+        rng = np.random.default_rng(n)
+        idx = np.unique(np.concatenate([rng.integers(0, n, 300), [0, n - 1]])).astype(np.uint64)
+        pb = t.generate_batch_proofs(np.concatenate([idx, [n, 2**50]]).astype(np.uint64))
+        L = len(want) - 1
+        if L:
+            assert (pb.positions[-2:] == 0xFFFFFFFF).all()
+            for q, i in enumerate(idx):
+                sib, pos = oracle.merkle_prove(want, n, arity, int(i))
+                assert (pb.siblings[q] == sib).all() and (pb.positions[q] == pos).all(), (arity, n, int(i))
+        good = gpu.MerkleProofBatch(pb.siblings[: idx.size], pb.positions[: idx.size], idx, arity)
+        vals = leaves[idx.astype(np.int64)].copy()
+        assert t.verify_batch_proofs(good, vals).all()
+        if idx.size > 1:
+            vals[1, 0] ^= 1
+            res = t.verify_batch_proofs(good, vals)
+            assert res[0] == 1 and res[1] == 0
+        l, r = synth_elements(1, 3000), synth_elements(2, 3000)
+        assert (mg.batch_hash_pairs(l, r) == oracle.hash_pairs(l, r)).all()
+        t.close()
+    finally:
+        mg.close()
+
+
+def test_sharded_tree_over_all_devices_nccl(gpu, oracle):
+    """One process driving every GPU of the box through cuzk_mg_init_local: the subtree roots cross NVLink in one NCCL
+    all-gather issued by the library; root == single-device full build == oracle, proofs served from the shards verify."""
+    import torch
+
+    ngpus = min(torch.cuda.device_count(), 8)
+    if ngpus < 2:
+        pytest.skip("needs at least two GPUs")
+    for arity, n in ((8, 300_000), (2, (1 << 16) + 3), (5, 40)):
+        leaves = synth_u64_leaves(80 + arity, n)
+        want = oracle.merkle_build(leaves, arity)
+        mg = gpu.MultiGpu.local(ngpus)
+        try:
+            t = mg.build_tree(leaves, arity=arity)
+            assert (t.get_root_hash() == want[-1][0]).all(), (arity, n)
+            single = gpu.DeviceMerkleTree(to_dev(leaves), arity=arity)
+            assert (single.get_root_hash() == t.get_root_hash()).all()
+            single.close()
+            rng = np.random.default_rng(arity)
+            idx = np.unique(np.concatenate([rng.integers(0, n, 12_000 if n > 1000 else 30), [0, n - 1]])).astype(np.uint64)
+            pb = t.generate_batch_proofs(idx)
+            for q in range(0, idx.size, max(1, idx.size // 50)):
+                sib, pos = oracle.merkle_prove(want, n, arity, int(idx[q]))
+                assert (pb.siblings[q] == sib).all() and (pb.positions[q] == pos).all(), (arity, n, int(idx[q]))
+            vals = leaves[idx.astype(np.int64)].copy()
+            assert t.verify_batch_proofs(pb, vals).all()
+            vals[0, 0] ^= 1
+            assert t.verify_batch_proofs(pb, vals)[0] == 0
+            l, r = synth_elements(5, 10_000), synth_elements(6, 10_000)
+            assert (mg.batch_hash_pairs(l, r) == oracle.hash_pairs(l, r)).all()
+            t.close()
+        finally:
+            mg.close()
 
 
 def test_fast_path_flags_are_sound(gpu, oracle):

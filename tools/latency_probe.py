@@ -1,33 +1,73 @@
 #!/usr/bin/env python
-"""Latency-bound cases for kernel variants: 4096 pair hashes per launch, 50K-leaf binary tree build, 5K proof verify.
-usage: latency_probe.py lib1.so [lib2.so ...]"""
-import os, sys
-import numpy as np, torch
+"""Latency-bound cases: pair-hash launches of 256 .. 32768 units on the cooperative and on the one-thread kernels (where do
+they cross?), the 50K-leaf binary build, 5K-proof verification, the 2^20-leaf 4-ary build.  usage: latency_probe.py [lib.so]"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from cuzk_b200 import lib as cl
 
+
 def timed(fn, reps):
-    fn(); torch.cuda.synchronize()
+    fn()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(reps): fn()
-    e1.record(); torch.cuda.synchronize()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 
-for path in sys.argv[1:]:
-    L = cl.Lib(path)
-    L.check(L.cuzk_init(0), "init")
+
+L = cl.Lib(sys.argv[1]) if len(sys.argv) > 1 else cl.get_lib()
+L.check(L.cuzk_init(0), "init")
+default_max = L.cuzk_debug_set_coop_max(0)
+L.cuzk_debug_set_coop_max(default_max)
+out = {"coop_max_default": default_max, "pairs_us": {}}
+nmax = 32768
+l = torch.empty((nmax, 4), dtype=torch.int64, device="cuda")
+r = torch.empty_like(l)
+o = torch.empty_like(l)
+L.cuzk_synth_elements(l.data_ptr(), nmax, 1, 0, 1, None)
+L.cuzk_synth_elements(r.data_ptr(), nmax, 2, 0, 1, None)
+for n in (256, 592, 1184, 1776, 2368, 3552, 4096, 4736, 5920, 7104, 8192, 12288, 16384, 32768):
     row = {}
-    for n in (1024, 4096, 16384):
-        l = torch.empty((n, 4), dtype=torch.int64, device="cuda"); r = torch.empty_like(l); o = torch.empty_like(l)
-        L.cuzk_synth_elements(l.data_ptr(), n, 1, 0, 1, None); L.cuzk_synth_elements(r.data_ptr(), n, 2, 0, 1, None)
-        row[f"pairs{n}_us"] = 1e3 * timed(lambda: L.cuzk_poseidon_hash_pairs(l.data_ptr(), r.data_ptr(), o.data_ptr(), n, 0, None), 50)
-    n = 50_000
+    for name, cm in (("cooperative", 1 << 30), ("one_thread", 0)):
+        L.cuzk_debug_set_coop_max(cm)
+        row[name] = round(1e3 * timed(lambda: L.cuzk_poseidon_hash_pairs(l.data_ptr(), r.data_ptr(), o.data_ptr(), n, 0, None), 30), 1)
+    out["pairs_us"][n] = row
+L.cuzk_debug_set_coop_max(default_max)
+for label, n, arity in (("build_50k_binary_ms", 50_000, 2), ("build_2p20_4ary_ms", 1 << 20, 4), ("build_2p23_8ary_ms", 1 << 23, 8)):
     leaves = torch.empty((n, 4), dtype=torch.int64, device="cuda")
     L.cuzk_synth_u64_leaves(leaves.data_ptr(), n, 3, 0, None)
-    tot = L.cuzk_merkle_total_nodes(n, 2)
+    tot = L.cuzk_merkle_total_nodes(n, arity)
     lv = torch.empty((tot, 4), dtype=torch.int64, device="cuda")
-    row["build50k_ms"] = timed(lambda: L.cuzk_merkle_build(leaves.data_ptr(), n, 2, lv.data_ptr(), 0, None), 10)
-    print(f"{os.path.basename(path):32s} " + "  ".join(f"{k}={v:8.3f}" for k, v in row.items()))
-    L.cuzk_shutdown()
+    row = {}
+    for name, cm in (("default", default_max), ("one_thread", 0), ("coop_8k", 8192)):
+        L.cuzk_debug_set_coop_max(cm)
+        row[name] = round(timed(lambda: L.cuzk_merkle_build(leaves.data_ptr(), n, arity, lv.data_ptr(), 0, None), 10), 3)
+    out[label] = row
+    if n == 50_000:
+        q, nlv = 5000, L.cuzk_merkle_num_levels(n, arity) - 1
+        idx = (torch.arange(q, dtype=torch.int64, device="cuda") * 7) % n
+        sib = torch.empty((q, nlv, arity - 1, 4), dtype=torch.int64, device="cuda")
+        pos = torch.empty((q, nlv), dtype=torch.int32, device="cuda")
+        res = torch.empty(q, dtype=torch.uint8, device="cuda")
+        L.check(L.cuzk_merkle_prove_batch(lv.data_ptr(), n, arity, idx.data_ptr(), q, sib.data_ptr(), pos.data_ptr(), 0, None), "prove")
+        vals = leaves[idx].contiguous()
+        row = {}
+        for name, cm in (("default", default_max), ("one_thread", 0), ("coop_8k", 8192)):
+            L.cuzk_debug_set_coop_max(cm)
+            row[name] = round(timed(lambda: L.cuzk_merkle_verify_batch(vals.data_ptr(), sib.data_ptr(), pos.data_ptr(), nlv, arity, lv[-1:].data_ptr(),
+                                                                       res.data_ptr(), q, 0, None), 10), 3)
+            assert bool(res.all())
+        out["verify_5k_binary_ms"] = row
+L.cuzk_debug_set_coop_max(default_max)
+print(json.dumps(out))
+L.cuzk_shutdown()

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""ncu target for the Merkle kernels: one 8-ary 2^24-leaf subtree-root pass (merkle_fused2_kernel + merkle_level_kernel),
+"""ncu target for the Merkle kernels: one 8-ary 2^24-leaf subtree-root pass (merkle_level_kernel, coop_merkle_level_kernel),
 one 4-ary 2^22-leaf full build, one 2^18-proof 4-ary batch verification.  Usage under ncu:
   ncu --set full --clock-control none -k regex:merkle_ -o gpurun_out/prof_merkle python tools/merkle_ncu_target.py"""
 import os

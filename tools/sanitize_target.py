@@ -35,8 +35,8 @@ for w in (1, 3, 8):
 for op, name in ((api.CudaFieldArithmetic.batch_add, "add"), (api.CudaFieldArithmetic.batch_subtract, "sub"), (api.CudaFieldArithmetic.batch_multiply, "mul")):
     assert (host(op(dev(l), dev(r))) == oracle.batch_fr(name, l, r)).all()
 assert (host(api.CudaFieldArithmetic.batch_power5(dev(l))) == oracle.batch_fr("pow5", l)).all()
-for fuse in (0, 1):
-    L.cuzk_debug_set_fuse(fuse)
+for coop_max in (0, 1 << 20):
+    L.cuzk_debug_set_coop_max(coop_max)
     for arity, m in ((2, 300), (4, 300), (8, 700)):
         leaves = synth_u64_leaves(5, m)
         want = oracle.merkle_build(leaves, arity)
@@ -45,7 +45,7 @@ for fuse in (0, 1):
         idx = torch.arange(0, m, 3, dtype=torch.int64, device="cuda")
         pb = t.generate_batch_proofs(idx)
         assert bool(t.verify_batch_proofs(pb, dev(leaves)[idx].contiguous()).all())
-L.cuzk_debug_set_fuse(0)
+L.cuzk_debug_set_coop_max(2368)
 trees = api.build_batch_trees(dev(synth_u64_leaves(6, 5 * 64)).reshape(5, 64, 4), arity=4)
 assert (host(trees[3].get_tree_levels()[-1])[0] == oracle.merkle_build(synth_u64_leaves(6, 5 * 64)[192:256], 4)[-1][0]).all()
 # grouped subtree-root pass (several real subtrees, height >= 3) + top levels
