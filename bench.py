@@ -563,7 +563,10 @@ def main():
         vals = shard[torch.from_numpy((pidx - np.uint64(l0)).astype(np.int64)).to(dev)].cpu().numpy().view(np.uint64)
         verdicts = tree.verify_batch_proofs(proofs, vals)
         proofs_ok = sharded_all_valid(torch.from_numpy(verdicts).to(dev)) and bool((proofs.positions != 0xFFFFFFFF).all())
-        perms = sum((1 << (3 * k)) * 4 for k in range(args.merkle_log2 // 3))   # nodes x ceil(8 / 2) permutations
+        perms, width = 0, nleaves                                                  # real nodes x ceil(8 / 2) permutations
+        while width > 1:
+            width = -(-width // 8)
+            perms += 4 * width
         merkle["octary_sharded"] = {"leaves": nleaves, "arity": 8, "n_gpus": world, "subtree_height": tree.subtree_height,
                                     "build_ms": ms, "leaves_per_s": nleaves / (ms * 1e-3),
                                     "scaling": "strong", "collective": "1 x ncclAllGather of 32 B subtree roots, issued by libcuzk_b200.so (cuzk_mg_tree_build)",

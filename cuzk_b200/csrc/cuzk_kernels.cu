@@ -109,6 +109,7 @@ const char *cuzk_last_error(void) { return g_err.c_str(); }
 const char *cuzk_version(void) { return "cuzk_b200 0.3 (sm_100a)"; }
 uint64_t cuzk_launch_count(void) { return g_launches.load(); }
 size_t cuzk_debug_set_coop_max(size_t units) { return g_coop_max.exchange(units); }
+size_t cuzk_debug_set_coop_wide_max(size_t units) { return g_coop_wide_max.exchange(units); }
 uint64_t cuzk_debug_fallback_count(void) {
   CtxGuard guard;
   if (!guard.get()) return ~0ull;
@@ -234,8 +235,8 @@ int cuzk_poseidon_hash_single(const uint64_t *in, uint64_t *out, size_t n, int m
   if (n == 0) return CUZK_OK;
   if (!in || !out) return fail(CUZK_ERR_INVALID, "null pointer");
   auto run = [](cudaStream_t st, const void *din, void *dout, size_t m) {
-    if (use_coop(m)) {
-      coop_hash_single_kernel<<<coop_grid(m), kCoopBlock, 0, st>>>(static_cast<const uint4 *>(din), static_cast<uint4 *>(dout), m);
+    if (const CoopKind kind = coop_kind(m)) {
+      CUZK_COOP_LAUNCH(kind, coop_hash_single_kernel, m, st, static_cast<const uint4 *>(din), static_cast<uint4 *>(dout), m);
       return check_launch("coop_hash_single_kernel");
     }
     hash_single_kernel<<<grid_for(m, kBlock), kBlock, 0, st>>>(static_cast<const uint4 *>(din), static_cast<uint4 *>(dout), m);
@@ -253,9 +254,9 @@ int cuzk_poseidon_hash_pairs(const uint64_t *left, const uint64_t *right, uint64
   if (n == 0) return CUZK_OK;
   if (!left || !right || !out) return fail(CUZK_ERR_INVALID, "null pointer");
   auto run = [](cudaStream_t st, const void *dl, const void *dr, void *dout, size_t m) {
-    if (use_coop(m)) {
-      coop_hash_pairs_kernel<<<coop_grid(m), kCoopBlock, 0, st>>>(static_cast<const uint4 *>(dl), static_cast<const uint4 *>(dr),
-                                                                 static_cast<uint4 *>(dout), m);
+    if (const CoopKind kind = coop_kind(m)) {
+      CUZK_COOP_LAUNCH(kind, coop_hash_pairs_kernel, m, st, static_cast<const uint4 *>(dl), static_cast<const uint4 *>(dr),
+                       static_cast<uint4 *>(dout), m);
       return check_launch("coop_hash_pairs_kernel");
     }
     hash_pairs_kernel<<<grid_for(m, kBlock), kBlock, 0, st>>>(static_cast<const uint4 *>(dl), static_cast<const uint4 *>(dr),
@@ -274,8 +275,8 @@ int cuzk_poseidon_permutation(uint64_t *states, size_t n, int mem, void *stream)
   if (n == 0) return CUZK_OK;
   if (!states) return fail(CUZK_ERR_INVALID, "null pointer");
   auto run = [](cudaStream_t st, void *d, size_t m) {
-    if (use_coop(m)) {
-      coop_permutation_kernel<<<coop_grid(m), kCoopBlock, 0, st>>>(static_cast<uint4 *>(d), m);
+    if (const CoopKind kind = coop_kind(m)) {
+      CUZK_COOP_LAUNCH(kind, coop_permutation_kernel, m, st, static_cast<uint4 *>(d), m);
       return check_launch("coop_permutation_kernel");
     }
     permutation_kernel<<<grid_for(m, kBlock), kBlock, 0, st>>>(static_cast<uint4 *>(d), m);
@@ -313,9 +314,9 @@ int cuzk_poseidon_sponge(const uint64_t *in, size_t width, uint64_t ds, uint64_t
   if (n == 0) return CUZK_OK;
   if (!out || (width && !in)) return fail(CUZK_ERR_INVALID, "null pointer");
   auto run = [&](cudaStream_t st, const void *din, void *dout, size_t m) {
-    if (use_coop(m)) {
-      coop_sponge_kernel<<<coop_grid(m), kCoopBlock, 0, st>>>(static_cast<const uint4 *>(din), (int)width, (u32)ds, (u32)(ds >> 32),
-                                                             static_cast<uint4 *>(dout), m);
+    if (const CoopKind kind = coop_kind(m)) {
+      CUZK_COOP_LAUNCH(kind, coop_sponge_kernel, m, st, static_cast<const uint4 *>(din), (int)width, (u32)ds, (u32)(ds >> 32),
+                       static_cast<uint4 *>(dout), m);
       return check_launch("coop_sponge_kernel");
     }
     sponge_kernel<<<grid_for(m, kBlock), kBlock, 0, st>>>(static_cast<const uint4 *>(din), (int)width, (u32)ds, (u32)(ds >> 32),
@@ -484,8 +485,8 @@ int cuzk_merkle_prove_batch(const uint64_t *levels, size_t n, unsigned arity, co
 // verification of m device-resident proofs on stream st (root from device memory, or by value when root == nullptr)
 static int verify_dev(const uint4 *leaves, const uint4 *sib, const u32 *pos, size_t levels, unsigned arity, const uint4 *root, uint4 root_lo,
                       uint4 root_hi, uint8_t *results, size_t m, cudaStream_t st) {
-  if (use_coop(m)) {
-    coop_merkle_verify_kernel<<<coop_grid(m), kCoopBlock, 0, st>>>(leaves, sib, pos, (int)levels, (int)arity, root, root_lo, root_hi, results, m);
+  if (const CoopKind kind = coop_kind(m)) {
+    CUZK_COOP_LAUNCH(kind, coop_merkle_verify_kernel, m, st, leaves, sib, pos, (int)levels, (int)arity, root, root_lo, root_hi, results, m);
     return check_launch("coop_merkle_verify_kernel");
   }
   merkle_verify_kernel<<<grid_for(m, kBlock), kBlock, 0, st>>>(leaves, sib, pos, (int)levels, (int)arity, root, root_lo, root_hi, results, m);
@@ -735,8 +736,8 @@ int cuzk_tree_update_leaves(cuzk_tree_t *t, const uint64_t *indices, const uint6
   u64 divisor = 1;
   while (p > 1) {
     divisor *= t->arity;
-    if (use_coop(count))
-      coop_merkle_update_level_kernel<<<coop_grid(count), kCoopBlock, 0, st>>>(cur, cur + 2 * p, di, count, t->n, divisor, (int)t->arity);
+    if (const CoopKind kind = coop_kind(count))
+      CUZK_COOP_LAUNCH(kind, coop_merkle_update_level_kernel, count, st, cur, cur + 2 * p, di, count, t->n, divisor, (int)t->arity);
     else
       merkle_update_level_kernel<<<grid_for(count, kBlock), kBlock, 0, st>>>(cur, cur + 2 * p, di, count, t->n, divisor, (int)t->arity);
     if ((rc = check_launch("merkle_update_level_kernel"))) return rc;

@@ -157,17 +157,36 @@ int check_launch(const char *what) {
   return CUZK_OK;
 }
 
-// ---- cooperative (sixteen lanes per unit) dispatch ----------------------------------------------------------------------
-// A launch of the one-thread-per-unit kernels takes one permutation latency (~186 us) however few units it has; the
-// cooperative kernels (coop_kernels.cuh) take a fraction of that while they fit the chip at about one warp per SM
-// sub-partition (148 x 4 warps x 2 units; measured on B200: 94 us up to 1184 units, 116 at 2368, 148 at 3552, 189 at 4736 against 187 us) and lose to the one-thread kernels once their larger instruction stream per unit
-// fills the issue slots.  Launchers switch at g_coop_max units (cuzk_debug_set_coop_max; 0 = never).
-#ifndef CUZK_COOP_MAX_DEFAULT
-#define CUZK_COOP_MAX_DEFAULT 3552
+// ---- cooperative (a group of lanes per unit) dispatch ------------------------------------------------------------------
+// A launch of the one-thread-per-unit kernels takes one permutation latency (~186 us) however few units it has.  The
+// cooperative kernels (coop_kernels.cuh) take a fraction of that while the chip is not full:
+//   Wide16  (16 lanes per unit, 2 units per warp): the lowest latency; used while the launch fits at about one warp per SM
+//           sub-partition (148 x 4 x 2 = 1184 units; measured 93 us there, 116 us at 2368, 189 us at 4736)
+//   Narrow8 (8 lanes per unit, 4 units per warp): fewer instructions per unit; used for the launches above that, until the
+//           one-thread kernels' 186 us win again
+// Thresholds: g_coop_wide_max and g_coop_max units (cuzk_debug_set_coop_wide_max / cuzk_debug_set_coop_max; coop_max 0 =
+// never cooperative).
+#ifndef CUZK_COOP_WIDE_MAX_DEFAULT
+#define CUZK_COOP_WIDE_MAX_DEFAULT 1184
 #endif
+#ifndef CUZK_COOP_MAX_DEFAULT
+#define CUZK_COOP_MAX_DEFAULT 6144
+#endif
+std::atomic<size_t> g_coop_wide_max{CUZK_COOP_WIDE_MAX_DEFAULT};
 std::atomic<size_t> g_coop_max{CUZK_COOP_MAX_DEFAULT};
-inline bool use_coop(size_t units) { return units != 0 && units <= g_coop_max.load(std::memory_order_relaxed); }
-inline unsigned coop_grid(size_t units) { return grid_for(units * 16, kCoopBlock); }
+enum CoopKind { kOneThread = 0, kWide16 = 1, kNarrow8 = 2 };
+inline CoopKind coop_kind(size_t units) {
+  if (units == 0 || units > g_coop_max.load(std::memory_order_relaxed)) return kOneThread;
+  return units <= g_coop_wide_max.load(std::memory_order_relaxed) ? kWide16 : kNarrow8;
+}
+inline bool use_coop(size_t units) { return coop_kind(units) != kOneThread; }
+inline unsigned coop_grid(size_t units, int lanes) { return grid_for(units * (size_t)lanes, kCoopBlock); }
+// launches kernel<Wide16> or kernel<Narrow8> over `units` units
+#define CUZK_COOP_LAUNCH(kind, kernel, units, st, ...)                                              \
+  do {                                                                                              \
+    if ((kind) == kWide16) kernel<Wide16><<<coop_grid(units, 16), kCoopBlock, 0, st>>>(__VA_ARGS__); \
+    else kernel<Narrow8><<<coop_grid(units, 8), kCoopBlock, 0, st>>>(__VA_ARGS__);                   \
+  } while (0)
 
 // ---- parallel host copies for pageable caller memory ----------------------------------------------------------------
 // cudaMemcpyAsync on pageable memory (a std::vector, which is what the reference's API hands us) is staged by the driver
@@ -469,9 +488,9 @@ int fr_batch_dev(int op, const uint64_t *a, const uint64_t *b, uint64_t *out, si
 int launch_level(const uint4 *in, uint4 *out, size_t in_real, size_t out_count, unsigned arity, const uint4 *pad_in, cudaStream_t st,
                  size_t ntrees = 1, size_t tree_stride = 0) {
   if (out_count * ntrees == 0) return CUZK_OK;
-  if (use_coop(out_count * ntrees)) {
-    coop_merkle_level_kernel<<<coop_grid(out_count * ntrees), kCoopBlock, 0, st>>>(in, out, in_real, out_count, (int)arity, pad_in,
-                                                                                  pad_in + 2, ntrees, tree_stride);
+  if (const CoopKind kind = coop_kind(out_count * ntrees)) {
+    CUZK_COOP_LAUNCH(kind, coop_merkle_level_kernel, out_count * ntrees, st, in, out, in_real, out_count, (int)arity, pad_in, pad_in + 2,
+                     ntrees, tree_stride);
     return check_launch("coop_merkle_level_kernel");
   }
   merkle_level_kernel<<<grid_for(out_count * ntrees, kBlock), kBlock, 0, st>>>(in, out, in_real, out_count, (int)arity, pad_in, pad_in + 2,

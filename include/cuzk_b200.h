@@ -257,10 +257,13 @@ int cuzk_synth_u64_leaves(uint64_t *out, size_t n, uint64_t seed, uint64_t start
  * canonical 3-element states; mode 0 = the production fast path with its exact fallback, 1 = exact path only */
 int cuzk_debug_mds_layer(uint64_t *states, size_t n, int mode, void *stream);
 
-/* Launches of at most `units` units (hashes, nodes, proofs, states) run on the cooperative kernels -- sixteen lanes per
- * permutation (csrc/coop.cuh), a fraction of the one-thread kernels' latency while the chip is not full -- larger ones on
- * the one-thread-per-unit kernels.  0 = never cooperative.  Returns the previous threshold.  Results are identical. */
+/* Launches of at most `units` units (hashes, nodes, proofs, states) run on the cooperative kernels -- one permutation spread
+ * over a group of lanes (csrc/coop.cuh), a fraction of the one-thread kernels' latency while the chip is not full -- larger
+ * ones on the one-thread-per-unit kernels.  0 = never cooperative.  Among the cooperative launches those of at most
+ * `wide` units use sixteen lanes per permutation (lowest latency), the others eight (fewer instructions per unit).
+ * Both return the previous threshold.  Results are identical on every path. */
 size_t cuzk_debug_set_coop_max(size_t units);
+size_t cuzk_debug_set_coop_wide_max(size_t wide);
 
 /* how many units (hashes, nodes, proof levels, states) were evaluated a second time on the exact path because the fast
  * path met a comparison its top-word test could not decide (about 1e-6 per permutation on random data); a blocking read */

@@ -1,5 +1,5 @@
-// coop_emul.cpp -- TEST INFRASTRUCTURE: runs the cooperative sixteen-lanes-per-permutation source (cuzk_b200/csrc/coop.cuh)
-// on the host, sixteen threads in lockstep standing in for the lanes of one group (shuffles and votes go through a
+// coop_emul.cpp -- TEST INFRASTRUCTURE: runs the cooperative lane-group source (cuzk_b200/csrc/coop.cuh; layout Wide16, or
+// Narrow8 with -DCUZK_EMUL_LANES=8) on the host, one thread per lane in lockstep (shuffles and votes go through a
 // shared exchange buffer and a spinning barrier), and compares every result with the plain-C oracle.  It checks the
 // arithmetic of the cooperative path -- in particular that a unit whose `unc` vote is clear is bit-exact -- without a GPU.
 //
@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../cuzk_b200/csrc/coop.cuh"
+#include "../../cuzk_b200/csrc/coop16.cuh"
 
 extern "C" {
 void cuzk_oracle_round_constants(uint64_t *out);
@@ -24,7 +25,10 @@ void cuzk_oracle_batch_mds_layer(uint64_t *states, size_t n);
 }
 
 namespace {
-constexpr int kLanes = 16;
+#ifndef CUZK_EMUL_LANES
+#define CUZK_EMUL_LANES 16
+#endif
+constexpr int kLanes = CUZK_EMUL_LANES;
 thread_local uint32_t tl_lane;
 std::atomic<uint32_t> g_count{0};
 std::atomic<uint32_t> g_gen{0};
@@ -46,17 +50,17 @@ void barrier() {
 
 namespace cuzk {
 namespace coop {
-u32 lane16() { return tl_lane; }
-u32 shfl(u32 x, u32 src) {
+u32 emul_lane() { return tl_lane; }
+u32 emul_shfl(u32 x, u32 src) {
   const uint32_t par = tl_parity;
   tl_parity ^= 1u;
   g_slot[par][tl_lane] = x;
   std::atomic_thread_fence(std::memory_order_seq_cst);
   barrier();
-  const u32 v = g_slot[par][src & 15u];
+  const u32 v = g_slot[par][src & (u32)(kLanes - 1)];
   return v;
 }
-u32 ballot16(bool p) {
+u32 emul_ballot(bool p) {
   const uint32_t par = tl_parity;
   tl_parity ^= 1u;
   g_slot[par][tl_lane] = p ? 1u : 0u;
@@ -70,6 +74,40 @@ u32 ballot16(bool p) {
 }  // namespace cuzk
 
 using namespace cuzk;
+#if CUZK_EMUL_LANES == 8
+typedef coop::Narrow8 Y;
+#else
+typedef coop::Wide16 Y;
+#endif
+// one interface over the templated algorithms (coop.cuh) and the non-templated sixteen-lane file the kernels use (coop16.cuh,
+// -DCUZK_EMUL_LEGACY16)
+#ifdef CUZK_EMUL_LEGACY16
+namespace impl {
+typedef coop16::Lane Lane;
+typedef coop16::Flags Flags;
+inline Lane make_lane() { return coop16::make_lane(); }
+inline void gather(u32 (&r)[8], u32 x) { coop16::gather(r, x); }
+inline void mulred1(u32 (&r)[1], const u32 (&a)[1][8], const u32 (&b)[1], const Lane &L, Flags &F) { coop16::mulred<1>(r, a, b, L, F); }
+inline void add_reduce1(u32 (&r)[1], const u32 (&a)[1], const u32 (&b)[1], const Lane &L, Flags &F) { coop16::add_reduce<1>(r, a, b, L, F); }
+template <class Rc> inline void permute(u32 (&s)[3], const Rc &rct, const Lane &L, Flags &F) { coop16::permute(s, rct, L, F); }
+template <class Rc, class Ld> inline u32 sponge(u32 &o, u32 a, u32 b, int w, const Rc &rct, const Lane &L, Ld ld) { return coop16::sponge(o, a, b, w, rct, L, ld); }
+inline void mds_arc(u32 (&s)[3], const u32 (&rc)[3], bool h, const Lane &L, Flags &F) { coop16::mds_arc(s, rc, h, L, F); }
+inline bool flagged(const Flags &F) { return coop16::flagged(F); }
+}  // namespace impl
+#else
+namespace impl {
+typedef coop::Lane Lane;
+typedef coop::Flags Flags;
+inline Lane make_lane() { return Y::make_lane(); }
+inline void gather(u32 (&r)[8], u32 x) { coop::gather<Y>(r, x); }
+inline void mulred1(u32 (&r)[1], const u32 (&a)[1][8], const u32 (&b)[1], const Lane &L, Flags &F) { coop::mulred<Y, 1>(r, a, b, L, F); }
+inline void add_reduce1(u32 (&r)[1], const u32 (&a)[1], const u32 (&b)[1], const Lane &L, Flags &F) { coop::add_reduce<Y, 1>(r, a, b, L, F); }
+template <class Rc> inline void permute(u32 (&s)[3], const Rc &rct, const Lane &L, Flags &F) { coop::permute<Y>(s, rct, L, F); }
+template <class Rc, class Ld> inline u32 sponge(u32 &o, u32 a, u32 b, int w, const Rc &rct, const Lane &L, Ld ld) { return coop::sponge<Y>(o, a, b, w, rct, L, ld); }
+inline void mds_arc(u32 (&s)[3], const u32 (&rc)[3], bool h, const Lane &L, Flags &F) { coop::mds_arc<Y>(s, rc, h, L, F); }
+inline bool flagged(const Flags &F) { return coop::flagged(F); }
+}  // namespace impl
+#endif
 
 namespace {
 uint32_t g_rc[192][2];
@@ -150,38 +188,38 @@ inline void put_word(uint64_t *el, u32 m, u32 v) {
 
 void lane_main(uint32_t lane) {
   tl_lane = lane;
-  const coop::Lane L = coop::make_lane();
+  const impl::Lane L = impl::make_lane();
   RcTable rct;
   for (auto &job : g_jobs) {
-    coop::Flags F;
+    impl::Flags F;
     u32 unc = 0;
     if (job.kind == 0) {
       u32 a[1][8], b[1], r[1];
-      coop::gather(a[0], word_of(&job.in[0], lane));
+      impl::gather(a[0], word_of(&job.in[0], lane));
       b[0] = word_of(&job.in[4], lane);
-      coop::mulred<1>(r, a, b, L, F);
+      impl::mulred1(r, a, b, L, F);
       put_word(job.out, lane, r[0]);
     } else if (job.kind == 1) {
       u32 a[1] = {word_of(&job.in[0], lane)}, b[1] = {word_of(&job.in[4], lane)}, r[1];
-      coop::add_reduce<1>(r, a, b, L, F);
+      impl::add_reduce1(r, a, b, L, F);
       put_word(job.out, lane, r[0]);
     } else if (job.kind == 2) {
       u32 s[3] = {word_of(&job.in[0], lane), word_of(&job.in[4], lane), word_of(&job.in[8], lane)};
-      coop::permute(s, rct, L, F);
+      impl::permute(s, rct, L, F);
       for (int i = 0; i < 3; ++i) put_word(job.out + 4 * i, lane, s[i]);
     } else if (job.kind == 3) {
       u32 out;
       const uint64_t *in = job.in.data();
-      const u32 vote = coop::sponge(out, 3u, 0u, job.width, rct, L, [&](int i) { return word_of(in + 4 * i, lane); });
+      const u32 vote = impl::sponge(out, 3u, 0u, job.width, rct, L, [&](int i) { return word_of(in + 4 * i, lane); });
       put_word(job.out, lane, out);
       unc = vote;
     } else {
       u32 s[3] = {word_of(&job.in[0], lane), word_of(&job.in[4], lane), word_of(&job.in[8], lane)};
       u32 rc[3] = {0, 0, 0};
-      coop::mds_arc(s, rc, false, L, F);
+      impl::mds_arc(s, rc, false, L, F);
       for (int i = 0; i < 3; ++i) put_word(job.out + 4 * i, lane, s[i]);
     }
-    const u32 vote = coop::ballot16(unc != 0 || coop::flagged(F));
+    const u32 vote = coop::emul_ballot(unc != 0 || impl::flagged(F));
     if (lane == 0) job.unc = vote;
   }
 }

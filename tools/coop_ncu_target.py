@@ -10,9 +10,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from cuzk_b200 import lib as cl  # noqa: E402
 
-L = cl.get_lib()
+L = cl.Lib(sys.argv[2]) if len(sys.argv) > 2 else cl.get_lib()
 L.check(L.cuzk_init(0), "init")
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+if len(sys.argv) > 3:
+    L.cuzk_debug_set_coop_max(1 << 30)
+    L.cuzk_debug_set_coop_wide_max(int(sys.argv[3]))
 l = torch.empty((n, 4), dtype=torch.int64, device="cuda")
 r = torch.empty_like(l)
 o = torch.empty_like(l)
