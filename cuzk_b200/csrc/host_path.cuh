@@ -160,17 +160,18 @@ int check_launch(const char *what) {
 // ---- cooperative (a group of lanes per unit) dispatch ------------------------------------------------------------------
 // A launch of the one-thread-per-unit kernels takes one permutation latency (~186 us) however few units it has.  The
 // cooperative kernels (coop_kernels.cuh) take a fraction of that while the chip is not full:
-//   Wide16  (16 lanes per unit, 2 units per warp): the lowest latency; used while the launch fits at about one warp per SM
-//           sub-partition (148 x 4 x 2 = 1184 units; measured 93 us there, 116 us at 2368, 189 us at 4736)
-//   Narrow8 (8 lanes per unit, 4 units per warp): fewer instructions per unit; used for the launches above that, until the
-//           one-thread kernels' 186 us win again
+//   Wide16  (16 lanes per unit, 2 units per warp): the lowest latency; measured 93 us up to 1184 units (one warp per SM
+//           sub-partition), 115 us up to 2368, 148 us at 3552, 189 us at 4736
+//   Narrow8 (8 lanes per unit, 4 units per warp): fewer instructions per unit; measured 138-141 us up to 2368 units, 166 us
+//           up to 4736, 215 us at 5920 -- the better choice between 2368 and 4736 units, where the one-thread kernels'
+//           186 us win again
 // Thresholds: g_coop_wide_max and g_coop_max units (cuzk_debug_set_coop_wide_max / cuzk_debug_set_coop_max; coop_max 0 =
 // never cooperative).
 #ifndef CUZK_COOP_WIDE_MAX_DEFAULT
-#define CUZK_COOP_WIDE_MAX_DEFAULT 1184
+#define CUZK_COOP_WIDE_MAX_DEFAULT 2368
 #endif
 #ifndef CUZK_COOP_MAX_DEFAULT
-#define CUZK_COOP_MAX_DEFAULT 6144
+#define CUZK_COOP_MAX_DEFAULT 4736
 #endif
 std::atomic<size_t> g_coop_wide_max{CUZK_COOP_WIDE_MAX_DEFAULT};
 std::atomic<size_t> g_coop_max{CUZK_COOP_MAX_DEFAULT};
