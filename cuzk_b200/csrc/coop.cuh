@@ -42,6 +42,10 @@
 #define CUZK_COOP_TAIL 2   // 2: two top-word rounds in the multiply tail; 3: one (both quotients from words fetched in one round; measured 4 % slower)
 #endif
 
+#ifndef CUZK_COOP_MDS_EXACT_CARRY
+#define CUZK_COOP_MDS_EXACT_CARRY 1   // 1: the carries of the MDS layer (up to 2^8 per word) are resolved exactly, see carry_exact
+#endif
+
 #ifdef CUZK_COOP_HOST_EMUL
 #define COOP_FN inline
 #else
@@ -363,6 +367,18 @@ COOP_FN u32 carry_pass(u32 lo, i32 c, const Lane &L, Flags &F) {
   return (u32)(u64)r;
 }
 
+// The same for non-negative carries, but exact whatever ripples: after the neighbour pass a word either generates a carry
+// (>= 2^32), propagates one (all ones) or absorbs it; two votes give those sets for the whole element and one integer add
+// plays the ripple (the carry into word g is bit g of ((G | P) + G) ^ P).  No flag.  Used where carries are large (the MDS
+// layer: up to 2^8, i.e. one unit in ~10^4 would flag on a single pass).
+template <class Y>
+COOP_FN u32 carry_exact(u32 lo, u32 c, const Lane &L) {
+  const u64 r = (u64)lo + (u64)(u32)Y::carry_in((i32)c, L);
+  const u32 G = ballot<Y::kLanes>((u32)(r >> 32) != 0u) & 0xffu, P = ballot<Y::kLanes>((u32)r == 0xFFFFFFFFu) & 0xffu;
+  const u32 cin = ((G | P) + G) ^ P;
+  return (u32)r + (L.low ? ((cin >> L.g) & 1u) : 0u);
+}
+
 // all eight words of a word-distributed element
 template <class Y>
 COOP_FN void gather(u32 (&r)[8], u32 x) {
@@ -514,11 +530,24 @@ COOP_FN void mds_arc(u32 (&s)[3], const u32 (&rc)[3], bool has_rc, const Lane &L
     const u32 q = word32(qhat - 5u * wsum[i]);
     const u64 y = Ls[i] + (u64)q * (u64)L.NP + (u64)rc[i];            // < 2^40: carries up to 2^8
     const u32 v7 = shfl<W>((u32)y, 7u) + shfl<W>((u32)(y >> 32), 6u);
+#if CUZK_COOP_MDS_EXACT_CARRY
+    // v7 is the true top word unless word 6 carries out after its own neighbour pass; the ripple it can receive from below
+    // is at most one, so a margin of one on word 6 covers every case: flag only there
+    {
+      const u64 r6 = (u64)(u32)y + (u64)(u32)Y::carry_in((i32)(u32)(y >> 32), L);
+      F.ovf |= (L.g == 6u && r6 >= 0xFFFFFFFFull) ? 1u : 0u;
+    }
+    const u32 ge = (v7 > CUZK_P7) ? 1u : 0u;                           // y < 2p: one conditional subtraction, decided by the top word
+    F.near = umin32(F.near, v7 ^ CUZK_P7);
+    const u64 z = y + (u64)(ge ? L.NP : 0u);                           // y - p as y + (W - p): mod W, lane values stay non-negative
+    s[i] = carry_exact<Y>((u32)z, (u32)(z >> 32), L);
+#else
     (void)carry_pass<Y>((u32)y, (i32)(u32)(y >> 32), L, F);           // flag only
     const u32 ge = (v7 > CUZK_P7) ? 1u : 0u;                           // y < 2p: one conditional subtraction, decided by the top word
     F.near = umin32(F.near, v7 ^ CUZK_P7);
     const i64 z = (i64)y - (i64)(u64)(ge ? L.P : 0u);
     s[i] = carry_pass<Y>((u32)(u64)z, (i32)(z >> 32), L, F);
+#endif
     // a state + constant whose top word reaches p's may need the reference's subtraction (arc_fast in poseidon.cuh):
     // lane 7 adds 2^32 - p7 and flags the carry
     if (has_rc) F.ovf |= (u32)(((u64)s[i] + (u64)L.arc) >> 32);

@@ -112,6 +112,14 @@ COOP_FN u32 carry_pass8(u32 lo, i32 c, const Lane &L, Flags &F) {
   return (u32)(u64)r;
 }
 
+// carry_pass8 for non-negative carries, exact whatever ripples (coop::carry_exact explains the two votes)
+COOP_FN u32 carry_exact8(u32 lo, u32 c, const Lane &L) {
+  const u64 r = (u64)lo + (u64)shfl(c, L.prev8);
+  const u32 G = ballot16((u32)(r >> 32) != 0u) & 0xffu, P = ballot16((u32)r == 0xFFFFFFFFu) & 0xffu;
+  const u32 cin = ((G | P) + G) ^ P;
+  return (u32)r + (L.low ? ((cin >> L.g) & 1u) : 0u);
+}
+
 // Top word (word 7) of the normalised value, read BEFORE its carry pass completes: lo_7 + c_6.  That is the exact word 7
 // whenever the carry pass of the same lane values raises no flag (by induction from lane 0 every carry c_g is then the true
 // carry out of word g), so callers run carry_pass8 on the side for its flag and do not wait for its result.
@@ -318,11 +326,22 @@ COOP_FN void mds_arc(u32 (&s)[3], const u32 (&rc)[3], bool has_rc, const Lane &L
     const u32 q = qhat - 5u * wsum[i];
     const u64 y = Ls[i] + (u64)q * (u64)L.NP + (u64)rc[i];            // < 2^40: carries up to 2^8
     const u32 v7 = top_word((u32)y, (i32)(u32)(y >> 32));
+#if CUZK_COOP_MDS_EXACT_CARRY
+    {   // v7 is the true top word unless word 6 carries out; a margin of one covers the ripple from below (coop.cuh, mds_arc)
+      const u64 r6 = (u64)(u32)y + (u64)shfl((u32)(y >> 32), L.prev8);
+      F.ovf |= (L.g == 6u && r6 >= 0xFFFFFFFFull) ? 1u : 0u;
+    }
+    const u32 ge = (v7 > CUZK_P7) ? 1u : 0u;                           // y < 2p: one conditional subtraction, decided by the top word
+    F.near = umin32(F.near, v7 ^ CUZK_P7);
+    const u64 z = y + (u64)(ge ? L.NP : 0u);                           // y - p as y + (W - p): mod W, lane values stay non-negative
+    s[i] = carry_exact8((u32)z, (u32)(z >> 32), L);
+#else
     (void)carry_pass8((u32)y, (i32)(u32)(y >> 32), L, F);   // flag only
     const u32 ge = (v7 > CUZK_P7) ? 1u : 0u;                           // y < 2p: one conditional subtraction, decided by the top word
     F.near = umin32(F.near, v7 ^ CUZK_P7);
     const i64 z = (i64)y - (i64)(u64)(ge ? L.P : 0u);
     s[i] = carry_pass8((u32)(u64)z, (i32)(z >> 32), L, F);
+#endif
     // a state + constant whose top word reaches p's may need the reference's subtraction (arc_fast in poseidon.cuh):
     // lane 7 adds 2^32 - p7 and flags the carry
     if (has_rc) F.ovf |= (u32)(((u64)s[i] + (u64)L.arc) >> 32);

@@ -20,7 +20,7 @@ constexpr int kPipeSlots = 4;                       // up to 3 inputs + 1 output
 constexpr size_t kHashChunk = 148 * CUZK_MIN_BLOCKS * CUZK_BLOCK / 2;   // half a resident wave of one-thread-per-hash CTAs per chunk
 constexpr size_t kCheapChunk = 1 << 20;             // element-wise field ops
 constexpr int kWsSlots = 6;
-constexpr int kSubtreeStreams = 4;
+constexpr int kSubtreeStreams = 16;   // internal streams per device; g_build_streams of them are used
 
 struct PinnedStage {   // per stream: pinned twins of the device staging buffers + "results are in the bounce buffer" event
   void *buf[kPipeSlots] = {};
@@ -173,6 +173,22 @@ int check_launch(const char *what) {
 #ifndef CUZK_COOP_MAX_DEFAULT
 #define CUZK_COOP_MAX_DEFAULT 4736
 #endif
+// Full-tree builds: a large tree is cut into g_build_groups groups of subtrees dealt over g_build_streams internal streams;
+// inside the groups only levels of at most g_group_coop_max nodes take the cooperative kernels (cuzk_debug_set_build_plan).
+// Measured (profiles/r02_build_plans.jsonl; 2^20 leaves arity 4 / 2^23 leaves arity 8 / 2^20 leaves arity 2, ms): one stream
+// 6.16 / 30.1 / 8.30; 4 groups 6.44 / 30.6 / 8.05; 8 groups, cap 1184: 5.82 / 29.7 / 7.85; 16 groups 7.3 / 31.9 / 9.5.
+#ifndef CUZK_BUILD_GROUPS_DEFAULT
+#define CUZK_BUILD_GROUPS_DEFAULT 8
+#endif
+#ifndef CUZK_BUILD_STREAMS_DEFAULT
+#define CUZK_BUILD_STREAMS_DEFAULT 8
+#endif
+#ifndef CUZK_GROUP_COOP_MAX_DEFAULT
+#define CUZK_GROUP_COOP_MAX_DEFAULT 1184
+#endif
+std::atomic<int> g_build_groups{CUZK_BUILD_GROUPS_DEFAULT};
+std::atomic<int> g_build_streams{CUZK_BUILD_STREAMS_DEFAULT};
+std::atomic<size_t> g_group_coop_max{CUZK_GROUP_COOP_MAX_DEFAULT};
 std::atomic<size_t> g_coop_wide_max{CUZK_COOP_WIDE_MAX_DEFAULT};
 std::atomic<size_t> g_coop_max{CUZK_COOP_MAX_DEFAULT};
 enum CoopKind { kOneThread = 0, kWide16 = 1, kNarrow8 = 2 };
@@ -486,10 +502,12 @@ int fr_batch_dev(int op, const uint64_t *a, const uint64_t *b, uint64_t *out, si
 }
 
 // one level for `ntrees` trees of identical shape: narrow launches go to the cooperative kernel
+// coop_cap: the widest level that may take the cooperative kernels (they cost 5-8x the instructions per node, which only
+// pays while the chip is otherwise idle; builds that run several groups side by side lower it)
 int launch_level(const uint4 *in, uint4 *out, size_t in_real, size_t out_count, unsigned arity, const uint4 *pad_in, cudaStream_t st,
-                 size_t ntrees = 1, size_t tree_stride = 0) {
+                 size_t ntrees = 1, size_t tree_stride = 0, size_t coop_cap = ~(size_t)0) {
   if (out_count * ntrees == 0) return CUZK_OK;
-  if (const CoopKind kind = coop_kind(out_count * ntrees)) {
+  if (const CoopKind kind = out_count * ntrees <= coop_cap ? coop_kind(out_count * ntrees) : kOneThread) {
     CUZK_COOP_LAUNCH(kind, coop_merkle_level_kernel, out_count * ntrees, st, in, out, in_real, out_count, (int)arity, pad_in, pad_in + 2,
                      ntrees, tree_stride);
     return check_launch("coop_merkle_level_kernel");
@@ -526,10 +544,11 @@ void subtree_streams_stop(Ctx &c) {
 // on the caller's stream after the groups have joined.  Every level is stored.
 // leaves: ntrees x n elements; levels_out: ntrees flat level-major trees of total_nodes(n) elements each.
 // padded_override (0 = derive from n) forces the padded leaf count (a power of arity >= n): shards of a larger tree.
-// allow_groups = false keeps everything on `st` (callers that run several builds on the internal streams themselves).
+// allow_groups = false keeps everything on `st` (callers that run several builds on the internal streams themselves; they
+// pass the cooperative cap for builds that run side by side as level_coop_cap).
 // pad_shift: the "leaves" are nodes of level pad_shift of a larger tree, so missing ones are the constant E_pad_shift.
 int merkle_build_dev(Ctx &c, const uint64_t *leaves, size_t n, unsigned arity, uint64_t *levels_out, cudaStream_t st, size_t ntrees = 1,
-                     size_t padded_override = 0, bool allow_groups = true, int pad_shift = 0) {
+                     size_t padded_override = 0, bool allow_groups = true, int pad_shift = 0, size_t level_coop_cap = ~(size_t)0) {
   const size_t padded = padded_override ? padded_override : cuzk_merkle_padded_leaves(n, arity);
   int nlv = 0;   // levels including the leaves
   size_t stride = 0;
@@ -546,39 +565,46 @@ int merkle_build_dev(Ctx &c, const uint64_t *leaves, size_t n, unsigned arity, u
                                                                           ntrees, stride);
   if ((rc = check_launch("merkle_pad_leaves_kernel"))) return rc;
 
-  // the cut: the tallest subtrees of which the real leaves still fill at least kSubtreeStreams; only for trees large enough
-  // that their lower levels are throughput-bound (several waves) while their upper ones are latency-bound
+  // the cut: the tallest subtrees of which the real leaves still fill the wanted number of groups; only for trees large
+  // enough that their lower levels are throughput-bound (several waves) while their upper ones are latency-bound
+  const size_t want_groups = (size_t)std::max(1, g_build_groups.load(std::memory_order_relaxed));
+  const int nstreams = std::min(kSubtreeStreams, std::max(1, g_build_streams.load(std::memory_order_relaxed)));
+  const size_t group_coop = g_group_coop_max.load(std::memory_order_relaxed);
   size_t span = 1;
   int cut = 0;   // levels [0, cut) are hashed group by group, the rest on the caller's stream
-  if (allow_groups && ntrees == 1 && c.sub_fork != nullptr && n >= ((size_t)1 << 17)) {
-    while (cut < nlv - 1 && ceil_div(n, span * arity) >= (size_t)kSubtreeStreams) {
+  if (allow_groups && ntrees == 1 && c.sub_fork != nullptr && want_groups >= 2 && n >= ((size_t)1 << 17)) {
+    while (cut < nlv - 1 && ceil_div(n, span * arity) >= want_groups) {
       span *= arity;
       ++cut;
     }
   }
   const size_t real_subtrees = ceil_div(n, span);
-  const size_t groups = cut >= 2 ? std::min<size_t>(real_subtrees, kSubtreeStreams) : 1;
+  const size_t groups = cut >= 2 ? std::min<size_t>(real_subtrees, want_groups) : 1;
   if (groups >= 2) {
     std::lock_guard<std::mutex> lk(c.sub_mu);
     CK(cudaEventRecord(c.sub_fork, st));
     const size_t total_subtrees = padded / span;
+    for (int g = 0; g < nstreams && (size_t)g < groups; ++g) CK(cudaStreamWaitEvent(c.sub_stream[g], c.sub_fork, 0));
     for (size_t g = 0; g < groups; ++g) {
       const size_t lo = real_subtrees * g / groups;
       const size_t hi = (g + 1 == groups) ? total_subtrees : real_subtrees * (g + 1) / groups;   // the last group also writes the padding nodes
-      cudaStream_t sg = c.sub_stream[g];
-      CK(cudaStreamWaitEvent(sg, c.sub_fork, 0));
+      cudaStream_t sg = c.sub_stream[g % nstreams];
       uint4 *cur = base;
       size_t p = padded, first = lo * span, width = (hi - lo) * span;   // this group's nodes on the current level
       size_t real = n > first ? std::min(n - first, width) : 0;
       for (int level = 0; level < cut; ++level) {
-        if ((rc = launch_level(cur + 2 * first, cur + 2 * p + 2 * (first / arity), real, width / arity, arity, pad + 2 * level, sg))) return rc;
+        if ((rc = launch_level(cur + 2 * first, cur + 2 * p + 2 * (first / arity), real, width / arity, arity, pad + 2 * level, sg, 1, 0,
+                               group_coop)))
+          return rc;
         cur += 2 * p;
         p /= arity;
         first /= arity;
         width /= arity;
         real = ceil_div(real, arity);
       }
-      CK(cudaEventRecord(c.sub_join[g], sg));
+    }
+    for (int g = 0; g < nstreams && (size_t)g < groups; ++g) {
+      CK(cudaEventRecord(c.sub_join[g], c.sub_stream[g]));
       CK(cudaStreamWaitEvent(st, c.sub_join[g], 0));
     }
   } else {
@@ -594,7 +620,7 @@ int merkle_build_dev(Ctx &c, const uint64_t *leaves, size_t n, unsigned arity, u
   }
   for (int level = cut; p > 1; ++level) {
     const size_t q = p / arity;
-    if ((rc = launch_level(cur, cur + 2 * p, real, q, arity, pad + 2 * level, st, ntrees, stride))) return rc;
+    if ((rc = launch_level(cur, cur + 2 * p, real, q, arity, pad + 2 * level, st, ntrees, stride, level_coop_cap))) return rc;
     cur += 2 * p;
     real = ceil_div(real, arity);
     p = q;
@@ -653,7 +679,7 @@ int subtree_roots_dev(Ctx &c, const uint64_t *leaves, size_t n, unsigned arity, 
   size_t span = 1;
   for (unsigned i = 0; i < height; ++i) span *= arity;
   const size_t real_subtrees = ceil_div(n, span);   // subtrees with at least one real leaf; the rest are padding constants
-  const size_t groups = std::min<size_t>(real_subtrees, kSubtreeStreams);
+  const size_t groups = std::min<size_t>(real_subtrees, (size_t)std::min(kSubtreeStreams, std::max(1, g_build_streams.load(std::memory_order_relaxed))));
   if (height < 3 || groups < 2 || c.sub_fork == nullptr) return subtree_roots_one_stream(c, leaves, n, arity, height, count, roots_out, st);
   std::lock_guard<std::mutex> lk(c.sub_mu);
   CK(cudaEventRecord(c.sub_fork, st));

@@ -397,7 +397,7 @@ int cuzk_mg_tree_build(cuzk_mg_t *mg, const uint64_t *const *local_leaves, size_
       const size_t nsub = hi - lo;
       bool used[kSubtreeStreams] = {};
       for (size_t s = 0; s < nsub; ++s) {
-        const int g = (int)(s % kSubtreeStreams);
+        const int g = (int)(s % (size_t)std::min(kSubtreeStreams, std::max(1, g_build_streams.load(std::memory_order_relaxed))));
         cudaStream_t sg = c.sub_stream[g];
         if (!used[g]) {
           if ((e = cudaStreamWaitEvent(sg, c.sub_fork, 0)) != cudaSuccess) return bail(cuda_fail(e, "cudaStreamWaitEvent"));
@@ -406,7 +406,9 @@ int cuzk_mg_tree_build(cuzk_mg_t *mg, const uint64_t *const *local_leaves, size_
         const size_t first = s * P.span;
         const size_t n_s = std::min(P.span, (l1 - l0) - first);
         uint64_t *dst = t->shard[r] + 4 * s * t->sub_total;
-        if ((rc = merkle_build_dev(c, leaves + 4 * first, n_s, arity, dst, sg, 1, P.span, /*allow_groups=*/false))) return bail(rc);
+        if ((rc = merkle_build_dev(c, leaves + 4 * first, n_s, arity, dst, sg, 1, P.span, /*allow_groups=*/false, 0,
+                                   nsub > 1 ? g_group_coop_max.load(std::memory_order_relaxed) : ~(size_t)0)))
+          return bail(rc);
         // the subtree's root goes straight into the all-gather send slot
         if ((e = cudaMemcpyAsync(t->gather_buf[r] + 4 * s, dst + 4 * (t->sub_total - 1), 32, cudaMemcpyDeviceToDevice, sg)) != cudaSuccess)
           return bail(cuda_fail(e, "cudaMemcpyAsync(root)"));

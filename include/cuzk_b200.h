@@ -264,6 +264,11 @@ int cuzk_debug_mds_layer(uint64_t *states, size_t n, int mode, void *stream);
  * Both return the previous threshold.  Results are identical on every path. */
 size_t cuzk_debug_set_coop_max(size_t units);
 size_t cuzk_debug_set_coop_wide_max(size_t wide);
+/* Full-tree builds (cuzk_merkle_build / cuzk_tree_build of one tree of >= 2^17 leaves): the tree is cut into `groups` groups
+ * of subtrees dealt round-robin over `streams` internal streams (<= 16); inside the groups only levels of at most
+ * `group_coop_max` nodes take the cooperative kernels.  groups / streams < 1 leave the value unchanged; groups = 1 builds level
+ * by level on the caller's stream.  Tuning and tests only. */
+void cuzk_debug_set_build_plan(int groups, int streams, size_t group_coop_max);
 
 /* how many units (hashes, nodes, proof levels, states) were evaluated a second time on the exact path because the fast
  * path met a comparison its top-word test could not decide (about 1e-6 per permutation on random data); a blocking read */

@@ -93,6 +93,7 @@ template <class Rc> inline void permute(u32 (&s)[3], const Rc &rct, const Lane &
 template <class Rc, class Ld> inline u32 sponge(u32 &o, u32 a, u32 b, int w, const Rc &rct, const Lane &L, Ld ld) { return coop16::sponge(o, a, b, w, rct, L, ld); }
 inline void mds_arc(u32 (&s)[3], const u32 (&rc)[3], bool h, const Lane &L, Flags &F) { coop16::mds_arc(s, rc, h, L, F); }
 inline bool flagged(const Flags &F) { return coop16::flagged(F); }
+inline u32 carry_exact(u32 lo, u32 c, const Lane &L) { return coop16::carry_exact8(lo, c, L); }
 }  // namespace impl
 #else
 namespace impl {
@@ -106,6 +107,7 @@ template <class Rc> inline void permute(u32 (&s)[3], const Rc &rct, const Lane &
 template <class Rc, class Ld> inline u32 sponge(u32 &o, u32 a, u32 b, int w, const Rc &rct, const Lane &L, Ld ld) { return coop::sponge<Y>(o, a, b, w, rct, L, ld); }
 inline void mds_arc(u32 (&s)[3], const u32 (&rc)[3], bool h, const Lane &L, Flags &F) { coop::mds_arc<Y>(s, rc, h, L, F); }
 inline bool flagged(const Flags &F) { return coop::flagged(F); }
+inline u32 carry_exact(u32 lo, u32 c, const Lane &L) { return coop::carry_exact<Y>(lo, c, L); }
 }  // namespace impl
 #endif
 
@@ -172,7 +174,7 @@ void gen_element(uint64_t &seed, uint64_t out[4], int kind) {
 }
 
 struct Job {
-  int kind;                       // 0 mul, 1 add, 2 permutation, 3 sponge, 4 mds layer
+  int kind;                       // 0 mul, 1 add, 2 permutation, 3 sponge, 4 mds layer, 5 exact carry resolution
   int width;
   std::vector<uint64_t> in;       // inputs (elements x 4)
   uint64_t out[12];
@@ -213,6 +215,9 @@ void lane_main(uint32_t lane) {
       const u32 vote = impl::sponge(out, 3u, 0u, job.width, rct, L, [&](int i) { return word_of(in + 4 * i, lane); });
       put_word(job.out, lane, out);
       unc = vote;
+    } else if (job.kind == 5) {
+      // lane values lo + 2^32 c: in[0..3] the low words, in[4..7] the carries
+      put_word(job.out, lane, impl::carry_exact(word_of(&job.in[0], lane), word_of(&job.in[4], lane), L));
     } else {
       u32 s[3] = {word_of(&job.in[0], lane), word_of(&job.in[4], lane), word_of(&job.in[8], lane)};
       u32 rc[3] = {0, 0, 0};
@@ -269,11 +274,26 @@ int main(int argc, char **argv) {
     for (int e = 0; e < nel; ++e) gen_element(seed, &j.in[4 * e], (int)(splitmix(seed) % 8));
     g_jobs.push_back(j);
   }
+  // carry resolution: words of all ones (propagate), near all ones (generate with a carry), zero and random; carries up to 2^9
+  for (int u = 0; u < units * 40; ++u) {
+    Job j;
+    j.kind = 5;
+    j.width = 0;
+    j.in.resize(8);
+    u32 *w = reinterpret_cast<u32 *>(j.in.data());
+    for (int g = 0; g < 8; ++g) {
+      const uint64_t r = splitmix(seed);
+      const u32 pick = (u32)(r % 6);
+      w[g] = pick <= 1 ? 0xFFFFFFFFu : (pick == 2 ? 0xFFFFFFFFu - (u32)((r >> 8) % 600) : (pick == 3 ? 0u : (u32)(r >> 16)));
+      w[8 + g] = (u32)((r >> 48) % ((r & 0x80) ? 3u : 513u));
+    }
+    g_jobs.push_back(j);
+  }
   std::vector<std::thread> th;
   for (uint32_t l = 0; l < (uint32_t)kLanes; ++l) th.emplace_back(lane_main, l);
   for (auto &t : th) t.join();
 
-  long checked[5] = {0}, flagged[5] = {0}, bad[5] = {0}, bad_flagged[5] = {0};
+  long checked[6] = {0}, flagged[6] = {0}, bad[6] = {0}, bad_flagged[6] = {0};
   for (auto &job : g_jobs) {
     uint64_t want[12];
     int nout = 4;
@@ -281,6 +301,16 @@ int main(int argc, char **argv) {
     else if (job.kind == 1) cuzk_oracle_fr_add(&job.in[0], &job.in[4], want);
     else if (job.kind == 2) { memcpy(want, job.in.data(), 96); cuzk_oracle_permutation(want); nout = 12; }
     else if (job.kind == 3) cuzk_oracle_batch_sponge(job.in.data(), (size_t)job.width, 3, want, 1);
+    else if (job.kind == 5) {   // sum_g (lo_g + 2^32 c_g) 2^(32 g) mod 2^256
+      const u32 *w = reinterpret_cast<const u32 *>(job.in.data());
+      u32 *o = reinterpret_cast<u32 *>(want);
+      uint64_t carry = 0;
+      for (int g = 0; g < 8; ++g) {
+        const uint64_t t = (uint64_t)w[g] + (g ? (uint64_t)w[8 + g - 1] : 0) + carry;
+        o[g] = (u32)t;
+        carry = t >> 32;
+      }
+    }
     else { memcpy(want, job.in.data(), 96); cuzk_oracle_batch_mds_layer(want, 1); nout = 12; }
     const bool same = memcmp(want, job.out, 8 * nout) == 0;
     ++checked[job.kind];
@@ -299,9 +329,9 @@ int main(int argc, char **argv) {
       }
     }
   }
-  const char *names[5] = {"multiply", "add", "permutation", "sponge", "mds_layer"};
+  const char *names[6] = {"multiply", "add", "permutation", "sponge", "mds_layer", "carry_exact"};
   long total_bad = 0;
-  for (int k = 0; k < 5; ++k) {
+  for (int k = 0; k < 6; ++k) {
     printf("{\"op\": \"%s\", \"checked\": %ld, \"flagged\": %ld, \"flagged_and_different\": %ld, \"unflagged_mismatches\": %ld}\n", names[k],
            checked[k], flagged[k], bad_flagged[k], bad[k]);
     total_bad += bad[k];

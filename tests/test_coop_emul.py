@@ -18,7 +18,7 @@ def _run(binary, units, seed, plain):
         subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "cpp"), binary])
     res = subprocess.run([path, str(units), str(seed), str(plain)], capture_output=True, text=True, timeout=600)
     rows = [json.loads(l) for l in res.stdout.splitlines() if l.startswith("{")]
-    assert res.returncode == 0 and len(rows) == 5, res.stdout[-2000:] + res.stderr[-2000:]
+    assert res.returncode == 0 and len(rows) == 6, res.stdout[-2000:] + res.stderr[-2000:]
     return rows
 
 

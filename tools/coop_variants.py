@@ -54,5 +54,22 @@ for path in sys.argv[2:]:
         L.cuzk_debug_set_coop_wide_max(wm)
         row[name] = {n: round(1e3 * timed(lambda: L.cuzk_poseidon_hash_pairs(l.data_ptr(), r.data_ptr(), o.data_ptr(), n, 0, None)), 1)
                      for n in (592, 1184, 2368, 4096, 6144, 8192)}
+    # how often a unit falls back to the exact path: 2^20 pair hashes per layout
+    big = 1 << 20
+    bl = torch.empty((big, 4), dtype=torch.int64, device="cuda")
+    br = torch.empty_like(bl)
+    bo = torch.empty_like(bl)
+    L.cuzk_synth_elements(bl.data_ptr(), big, 11, 0, 1, None)
+    L.cuzk_synth_elements(br.data_ptr(), big, 12, 0, 1, None)
+    row["fallbacks_per_2p20"] = {}
+    for name, wm in (("wide16", 1 << 30), ("narrow8", 0), ("one_thread", None)):
+        L.cuzk_debug_set_coop_max(0 if wm is None else 1 << 30)
+        L.cuzk_debug_set_coop_wide_max(wm or 0)
+        torch.cuda.synchronize()
+        before = L.cuzk_debug_fallback_count()
+        L.check(L.cuzk_poseidon_hash_pairs(bl.data_ptr(), br.data_ptr(), bo.data_ptr(), big, 0, None), "pairs")
+        torch.cuda.synchronize()
+        row["fallbacks_per_2p20"][name] = L.cuzk_debug_fallback_count() - before
+        row.setdefault("digest", {})[name] = int(bo.sum().item()) & 0xFFFFFFFF
     print(json.dumps(row))
     L.cuzk_shutdown()
