@@ -387,6 +387,25 @@ def main():
     b4096_pageable = harness(pl.ctypes.data, pr.ctypes.data, po.ctypes.data)
     harness_ok = bool((po[-256:] == sets[0][2][-256:].cpu().numpy()).all())
 
+    # ---- latency of one launch narrower than the chip (device resident; what bounds upper tree levels and small batches) ----
+    def launch_us(units, reps=20):
+        l, r, o = sets[0]
+        L.check(L.cuzk_poseidon_hash_pairs(l.data_ptr(), r.data_ptr(), o.data_ptr(), units, 0, sp), "pairs")
+        torch.cuda.synchronize(dev)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(reps):
+            L.check(L.cuzk_poseidon_hash_pairs(l.data_ptr(), r.data_ptr(), o.data_ptr(), units, 0, sp), "pairs")
+        a1.record(stream)
+        torch.cuda.synchronize(dev)
+        return round(a0.elapsed_time(a1) / reps * 1e3, 1)
+
+    latency = {"unit": "us per launch of N pair hashes, back to back on one stream",
+               "cooperative": {str(u): launch_us(u) for u in (1, 1184, 2368, 4096)}}
+    prev_coop = L.cuzk_debug_set_coop_max(0)
+    latency["one_thread_per_hash"] = {str(u): launch_us(u) for u in (1, 4096)}
+    L.cuzk_debug_set_coop_max(prev_coop)
+
     # ---- configs[4]: single / pair / sponge(8) hashing sweep over 2^16 .. 2^28 inputs (whole job; each rank its slice) ----
     sweep = None
     if not args.no_sweep:
@@ -630,7 +649,7 @@ def main():
                                  "api": "the same call on pageable memory (numpy / std::vector), staged by the library through pinned bounce buffers"},
                     "reference_harness_batch4096": {"value": b4096_value, "pageable": b4096_pageable, "unit": UNIT, "calls": -(-n // b),
                                                     "checked": harness_ok,
-                                                    "note": "245 synchronous host calls of <= 4096 pairs; each call runs on the cooperative kernels"}},
+                                                    "note": "245 synchronous host calls of <= 4096 pairs; each call is one cooperative-kernel launch that reads and writes pinned host memory directly (pageable: through a pinned bounce copy)"}},
             "gpu_launches": int(launches),
             "roofline": {"bound": "imad", "kernel": "hash_pairs_kernel", "achieved": achieved / 1e12, "peak": imad_peak / 1e12,
                          "unit": "T multiply-adds/s (32x32->64)", "frac": achieved / imad_peak, "traffic": ncu_traffic(),
@@ -649,6 +668,7 @@ def main():
             "clocks": clocks,
             "merkle": merkle,
             "sweep": sweep,
+            "latency": latency,
             "sweep_note": "configs[4]: inputs over the whole job, device resident, each rank hashes its contiguous slice; hashes/s aggregate",
         }
         sys.stdout.flush()

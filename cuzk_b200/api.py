@@ -524,7 +524,10 @@ class MultiGpu:
         import torch.distributed as dist
 
         lib = get_lib()
-        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        if dist.is_available() and dist.is_initialized():
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            rank, world = 0, 1      # a single process without a process group: one rank, no collective
         if device is None:
             device = torch.cuda.current_device()
         box = [None]

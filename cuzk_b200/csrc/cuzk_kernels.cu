@@ -110,6 +110,7 @@ const char *cuzk_version(void) { return "cuzk_b200 0.3 (sm_100a)"; }
 uint64_t cuzk_launch_count(void) { return g_launches.load(); }
 size_t cuzk_debug_set_coop_max(size_t units) { return g_coop_max.exchange(units); }
 size_t cuzk_debug_set_coop_wide_max(size_t units) { return g_coop_wide_max.exchange(units); }
+size_t cuzk_debug_set_direct_max(size_t bytes) { return g_direct_max.exchange(bytes); }
 void cuzk_debug_set_build_plan(int groups, int streams, size_t group_coop_max) {
   if (groups >= 1) g_build_groups.store(groups);
   if (streams >= 1) g_build_streams.store(streams > kSubtreeStreams ? kSubtreeStreams : streams);

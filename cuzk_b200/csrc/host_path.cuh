@@ -366,6 +366,25 @@ int bulk_download(Ctx &c, void *host, const void *dev, size_t bytes, cudaStream_
   return CUZK_OK;
 }
 
+// Small host-buffer calls skip the copy engines: the kernel reads its inputs from, and writes its results to, pinned host
+// memory through PCIe (the caller's own buffers when they are pinned, pinned bounce copies of pageable ones).  A 4096-pair
+// call moves 384 KiB -- a few microseconds of PCIe -- while two uploads, a download and the engine hand-overs between them
+// cost ~60 us on top of a ~170 us kernel (profiles/r02_tuning_notes.md).  cuzk_debug_set_direct_max(0) turns it off.
+#ifndef CUZK_DIRECT_MAX_DEFAULT
+#define CUZK_DIRECT_MAX_DEFAULT ((size_t)1 << 20)
+#endif
+constexpr size_t kDirectBounceMin = (size_t)1 << 20;   // bounce buffers are not re-allocated call by call as batches grow
+std::atomic<size_t> g_direct_max{CUZK_DIRECT_MAX_DEFAULT};   // bytes (inputs + outputs) up to which a call goes direct
+// the device's address of pinned / registered host memory, nullptr for anything else
+inline void *device_alias(const void *host) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, host) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return attr.type == cudaMemoryTypeHost ? attr.devicePointer : nullptr;
+}
+
 // Chunked, multi-stream host->device->host pass.  `nin` input arrays of `in_bytes[k]` bytes per unit, one output
 // array of `out_bytes` per unit (out may alias in[0] for in-place ops).  launch(stream, d_in[], d_out, m) enqueues the
 // kernel(s) for m units.  Returns after every result byte is in `out`.
@@ -388,6 +407,34 @@ int host_pipeline(Ctx &c, size_t n, size_t chunk, int nin, const void *const *in
     size_t widest = out_bytes;
     for (int k = 0; k < nin; ++k) widest = std::max(widest, in_bytes[k]);
     chunk = std::max<size_t>(1, std::min(chunk, ((size_t)16 << 20) / widest));
+  }
+  if (n * unit_bytes <= g_direct_max.load(std::memory_order_relaxed)) {
+    void *d_in[kPipeSlots] = {};
+    bool bounced0 = false;
+    for (int k = 0; k < nin; ++k) {
+      d_in[k] = device_alias(in[k]);
+      if (d_in[k] == nullptr) {
+        if ((rc = pin_reserve(c.pin[0].buf[k], c.pin[0].cap[k], std::max(n * in_bytes[k], kDirectBounceMin)))) return rc;
+        memcpy(c.pin[0].buf[k], in[k], n * in_bytes[k]);
+        d_in[k] = device_alias(c.pin[0].buf[k]);
+        if (k == 0) bounced0 = true;
+      }
+    }
+    void *d_out = out_aliases_in0 ? d_in[0] : device_alias(out);
+    const bool bounced_out = out_aliases_in0 ? bounced0 : d_out == nullptr;
+    if (!out_aliases_in0 && bounced_out) {
+      if ((rc = pin_reserve(c.pin[0].buf[kPipeSlots - 1], c.pin[0].cap[kPipeSlots - 1], std::max(n * out_bytes, kDirectBounceMin)))) return rc;
+      d_out = device_alias(c.pin[0].buf[kPipeSlots - 1]);
+    }
+    bool mapped = d_out != nullptr;
+    for (int k = 0; k < nin; ++k) mapped = mapped && d_in[k] != nullptr;
+    if (mapped) {
+      if ((rc = launch(c.stream[0], d_in, d_out, n))) return rc;
+      CK(cudaStreamSynchronize(c.stream[0]));
+      if (bounced_out) memcpy(out, out_aliases_in0 ? c.pin[0].buf[0] : c.pin[0].buf[kPipeSlots - 1], n * out_bytes);
+      return CUZK_OK;
+    }
+    // pinned memory this device cannot address: the copy path below
   }
   for (int s = 0; s < kPipeStreams; ++s) {
     for (int k = 0; k < nin; ++k)

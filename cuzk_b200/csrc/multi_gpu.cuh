@@ -390,8 +390,21 @@ int cuzk_mg_tree_build(cuzk_mg_t *mg, const uint64_t *const *local_leaves, size_
       leaves = static_cast<const uint64_t *>(staged);
     }
     if (!leaves) return bail(fail(CUZK_ERR_INVALID, "cuzk_mg_tree_build: missing leaves of a local shard"));
-    // one stream per subtree group: the narrow upper levels of one subtree hide behind the wide levels of the next
-    {
+    const size_t nsub_here = hi - lo;
+    if (nsub_here <= 2) {
+      // one or two large subtrees: one after the other on the handle's stream, each cut into groups over the internal streams
+      // by merkle_build_dev itself
+      for (size_t s = 0; s < nsub_here; ++s) {
+        const size_t first = s * P.span;
+        const size_t n_s = std::min(P.span, (l1 - l0) - first);
+        uint64_t *dst = t->shard[r] + 4 * s * t->sub_total;
+        if ((rc = merkle_build_dev(c, leaves + 4 * first, n_s, arity, dst, st, 1, P.span, /*allow_groups=*/true))) return bail(rc);
+        if ((e = cudaMemcpyAsync(t->gather_buf[r] + 4 * s, dst + 4 * (t->sub_total - 1), 32, cudaMemcpyDeviceToDevice, st)) != cudaSuccess)
+          return bail(cuda_fail(e, "cudaMemcpyAsync(root)"));
+      }
+    } else {
+      // several subtrees: dealt over the internal streams, so that the narrow upper levels of one hide behind the wide levels
+      // of the next
       std::lock_guard<std::mutex> lk(c.sub_mu);
       if ((e = cudaEventRecord(c.sub_fork, st)) != cudaSuccess) return bail(cuda_fail(e, "cudaEventRecord"));
       const size_t nsub = hi - lo;

@@ -91,6 +91,7 @@ _SIGS = {
     "cuzk_debug_set_coop_max": (C.c_size_t, [C.c_size_t]),
     "cuzk_debug_set_coop_wide_max": (C.c_size_t, [C.c_size_t]),
     "cuzk_debug_set_build_plan": (None, [C.c_int, C.c_int, C.c_size_t]),
+    "cuzk_debug_set_direct_max": (C.c_size_t, [C.c_size_t]),
     "cuzk_fr_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "cuzk_poseidon_hash_single": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "cuzk_poseidon_hash_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),

@@ -269,6 +269,10 @@ size_t cuzk_debug_set_coop_wide_max(size_t wide);
  * `group_coop_max` nodes take the cooperative kernels.  groups / streams < 1 leave the value unchanged; groups = 1 builds level
  * by level on the caller's stream.  Tuning and tests only. */
 void cuzk_debug_set_build_plan(int groups, int streams, size_t group_coop_max);
+/* Host-buffer calls that move at most `bytes` (inputs + outputs) run their kernel directly on pinned host memory -- the
+ * caller's buffers when they are pinned, pinned bounce copies otherwise -- instead of staging through device buffers
+ * (default 1 MiB; 0 = always stage).  Returns the previous value.  Tuning and tests only. */
+size_t cuzk_debug_set_direct_max(size_t bytes);
 
 /* how many units (hashes, nodes, proof levels, states) were evaluated a second time on the exact path because the fast
  * path met a comparison its top-word test could not decide (about 1e-6 per permutation on random data); a blocking read */

@@ -788,6 +788,75 @@ def test_large_host_batches_take_the_staged_path(gpu, oracle):
     assert (out == dev).all()
 
 
+def test_gpu_against_the_compiled_reference_itself(gpu, ref):
+    """The other tests compare with the plain-C port (which the CPU suite pins to the reference); this one compares the GPU
+    with the reference's own CPU classes, compiled unmodified into oracle/_ref/libcuzk_ref.so, directly: PoseidonHash pair
+    hashes and sponges on arbitrary 256-bit inputs, the permutation, and a NaryMerkleTree (root, proofs, verification)."""
+    rng = np.random.default_rng(2718)
+    h = gpu.CudaPoseidonHash()
+    n = 3000
+    l, r = rnd(rng, n, False), rnd(rng, n, False)
+    l[:EDGE.shape[0]] = EDGE
+    assert (to_host(h.batch_hash_pairs(to_dev(l), to_dev(r))) == ref.hash_pairs(l, r)).all()
+    for width in (1, 3, 4, 7, 8):
+        x = rnd(rng, 200 * width, False)
+        assert (to_host(h.batch_sponge(to_dev(x), width, 3)) == ref.sponge(x, width, 3)).all(), width
+    st = rnd(rng, 3 * 500, False).reshape(-1, 3, 4)
+    assert (to_host(h.batch_permutation(to_dev(st.copy()))) == ref.permutation(st)).all()
+    for arity, nleaves in ((2, 1000), (4, 777), (8, 4097)):
+        leaves = synth_u64_leaves(90 + arity, nleaves)
+        cpu = ref.tree(leaves, arity)
+        t = gpu.CudaNaryMerkleTree(to_dev(leaves), arity=arity)
+        assert (t.get_root_hash().reshape(-1) == cpu.root()).all(), arity
+        idx = np.unique(np.r_[0, nleaves - 1, rng.integers(0, nleaves, 40)])
+        pb = t.generate_batch_proofs(idx)
+        sib, pos = to_host(pb.siblings), pb.positions.cpu().numpy().view(np.uint32)
+        for k, i in enumerate(idx):
+            rs, rp = cpu.prove(int(i))
+            assert (sib[k] == rs).all() and (pos[k] == rp).all(), (arity, i)
+            assert cpu.verify(leaves[i], sib[k], pos[k].astype(np.uint64), cpu.root())      # the reference accepts the GPU's proof
+        assert bool(t.verify_batch_proofs(pb, to_dev(leaves[idx])).cpu().numpy().all())     # and the GPU the reference's (same bytes)
+
+
+@pytest.mark.parametrize("direct", [True, False])
+def test_small_host_calls_direct_on_pinned_memory_and_staged_agree(gpu, oracle, direct):
+    """Host-buffer calls of at most 1 MiB run their kernel directly on pinned host memory (the caller's own when it is pinned,
+    a bounce copy of pageable memory); cuzk_debug_set_direct_max(0) forces the staged copy path.  Same results either way, in
+    place for the permutation, for pinned and pageable callers, for the cooperative and the one-thread kernels."""
+    import torch
+
+    from cuzk_b200.lib import get_lib
+
+    L = get_lib()
+    rng = np.random.default_rng(77)
+    prev = L.cuzk_debug_set_direct_max((1 << 20) if direct else 0)
+    try:
+        h = gpu.CudaPoseidonHash()
+        for n in (1, 37, 4096, 9000):
+            l, r = rnd(rng, n, False), rnd(rng, n, False)
+            want = oracle.hash_pairs(l, r)
+            assert (h.batch_hash_pairs(l, r) == want).all(), ("pageable", n)          # numpy: pageable
+            pl, pr = torch.from_numpy(l.view(np.int64)).pin_memory(), torch.from_numpy(r.view(np.int64)).pin_memory()
+            po = torch.empty_like(pl).pin_memory()
+            L.check(L.cuzk_poseidon_hash_pairs(pl.data_ptr(), pr.data_ptr(), po.data_ptr(), n, 1, None), "pairs")   # CUZK_MEM_HOST
+            assert (po.numpy().view(np.uint64) == want).all(), ("pinned", n)
+            # pinned inputs, pageable output
+            out = np.zeros((n, 4), dtype=np.uint64)
+            L.check(L.cuzk_poseidon_hash_pairs(pl.data_ptr(), pr.data_ptr(), out.ctypes.data, n, 1, None), "pairs")
+            assert (out == want).all(), ("mixed", n)
+        m = 1500
+        st = rnd(rng, 3 * m, False)
+        want = oracle.permutation(st.reshape(-1, 3, 4))
+        assert (h.batch_permutation(st.copy()) == want).all()
+        ps = torch.from_numpy(st.view(np.int64).copy()).pin_memory()
+        L.check(L.cuzk_poseidon_permutation(ps.data_ptr(), m, 1, None), "permutation")
+        assert (ps.numpy().view(np.uint64).reshape(-1, 3, 4) == want).all()
+        x = rnd(rng, 5 * 700, False)
+        assert (h.batch_sponge(x, 5, 3) == oracle.sponge(x, 5, 3)).all()
+    finally:
+        L.cuzk_debug_set_direct_max(prev)
+
+
 @pytest.mark.parametrize("arity", [2, 3, 8])
 def test_device_tree_append_equals_fresh_build(gpu, oracle, arity):
     """cuzk_tree_append_leaves (NaryMerkleTree::insert_leaf, batched): appending within the padded level (path re-hash),
