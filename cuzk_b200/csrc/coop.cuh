@@ -42,6 +42,12 @@
 #define CUZK_COOP_TAIL 2   // 2: two top-word rounds in the multiply tail; 3: one (both quotients from words fetched in one round; measured 4 % slower)
 #endif
 
+#ifndef CUZK_COOP_RC_PREFETCH
+#define CUZK_COOP_RC_PREFETCH 1   // 1: round constants are fetched before the S-box and selected after it (see permute)
+#endif
+#ifndef CUZK_COOP_MDS_LOCAL_TOP
+#define CUZK_COOP_MDS_LOCAL_TOP 1   // 1: the MDS layer's top word is computed locally from lanes 7 and 6 of the sums (see mds_arc)
+#endif
 #ifndef CUZK_COOP_MDS_EXACT_CARRY
 #define CUZK_COOP_MDS_EXACT_CARRY 1   // 1: the carries of the MDS layer (up to 2^8 per word) are resolved exactly, see carry_exact
 #endif
@@ -517,6 +523,11 @@ COOP_FN void mds_arc(u32 (&s)[3], const u32 (&rc)[3], bool has_rc, const Lane &L
   const u32 pk7 = shfl<W>(pk, 7u), pk6 = shfl<W>(pk, 6u);
 #pragma unroll
   for (int i = 0; i < 3; ++i) l7[i] = shfl<W>((u32)Ls[i], 7u);
+#if CUZK_COOP_MDS_LOCAL_TOP
+  u32 l6[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) l6[i] = shfl<W>((u32)Ls[i], 6u);
+#endif
   u32 wsum[3];
   Y::wrap_sums(wsum, s7, s6, L, F);
 #pragma unroll
@@ -529,7 +540,15 @@ COOP_FN void mds_arc(u32 (&s)[3], const u32 (&rc)[3], bool has_rc, const Lane &L
     const u32 qhat = umulhi32(lp, kQuotMagic) >> 25;
     const u32 q = word32(qhat - 5u * wsum[i]);
     const u64 y = Ls[i] + (u64)q * (u64)L.NP + (u64)rc[i];            // < 2^40: carries up to 2^8
+#if CUZK_COOP_MDS_LOCAL_TOP
+    // the top word of y from the two top lane values, computed by every lane itself (the constant has no words above 1):
+    // one communication round less than fetching them from lanes 7 and 6 after y is known
+    const u64 y7 = ((u64)((pk7 >> (8 * i)) & 0xffu) << 32 | (u64)l7[i]) + (u64)q * (u64)CUZK_NP7;
+    const u64 y6 = ((u64)((pk6 >> (8 * i)) & 0xffu) << 32 | (u64)l6[i]) + (u64)q * (u64)CUZK_NP6;
+    const u32 v7 = (u32)y7 + (u32)(y6 >> 32);
+#else
     const u32 v7 = shfl<W>((u32)y, 7u) + shfl<W>((u32)(y >> 32), 6u);
+#endif
 #if CUZK_COOP_MDS_EXACT_CARRY
     // v7 is the true top word unless word 6 carries out after its own neighbour pass; the ripple it can receive from below
     // is at most one, so a margin of one on word 6 covers every case: flag only there
@@ -572,9 +591,31 @@ COOP_FN void permute(u32 (&s)[3], const RcTable &rct, const Lane &L, Flags &F) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) s[i] = t[i];
   }
+#if CUZK_COOP_RC_PREFETCH
+  u32 pick0 = (L.g == 0u) ? 0xffffffffu : 0u, pick1 = (L.g == 1u) ? 0xffffffffu : 0u;   // lanes 0 and 1 hold the two words of a constant
+  coop::pin_register(pick0);
+  coop::pin_register(pick1);
+#endif
 #pragma unroll 1
   for (int round = 0; round < 64; ++round) {
     const bool full = (round < 4) || (round >= 60);
+    const bool has_rc = round < 63;
+#if CUZK_COOP_RC_PREFETCH
+    // the next round's constants: both words of each, fetched by every lane with a uniform index BEFORE the S-box and
+    // selected by lane after it, so the ~50-cycle constant loads (and no divergent branch around them) hide behind the S-box;
+    // fetched after it they were 12 % of the kernel's time (profiles/r02_tuning_notes.md)
+    u32 cw[3][2];
+    {
+      const int next = 3 * (has_rc ? round + 1 : round);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        cw[i][0] = rct(next + i, 0);
+        cw[i][1] = rct(next + i, 1);
+        coop::pin_register(cw[i][0]);
+        coop::pin_register(cw[i][1]);
+      }
+    }
+#endif
     if (full) {
       sbox<Y, 3>(s, L, F);
     } else {
@@ -583,9 +624,14 @@ COOP_FN void permute(u32 (&s)[3], const RcTable &rct, const Lane &L, Flags &F) {
       s[0] = x[0];
     }
     u32 rc[3];
-    const bool has_rc = round < 63;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) rc[i] = has_rc ? rc_word(rct, 3 * (round + 1) + i, L.g) : 0u;
+    for (int i = 0; i < 3; ++i) {
+#if CUZK_COOP_RC_PREFETCH
+      rc[i] = ((cw[i][0] & pick0) | (cw[i][1] & pick1)) & (has_rc ? 0xffffffffu : 0u);   // masks, not selects: ptxas turns the selects into branches
+#else
+      rc[i] = has_rc ? rc_word(rct, 3 * (round + 1) + i, L.g) : 0u;
+#endif
+    }
     mds_arc<Y>(s, rc, has_rc, L, F);
   }
 }

@@ -306,6 +306,11 @@ COOP_FN void mds_arc(u32 (&s)[3], const u32 (&rc)[3], bool has_rc, const Lane &L
   const u32 pk7 = shfl(pk, 7u), pk6 = shfl(pk, 6u);
 #pragma unroll
   for (int i = 0; i < 3; ++i) l7[i] = shfl((u32)Ls[i], 7u);
+#if CUZK_COOP_MDS_LOCAL_TOP
+  u32 l6[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) l6[i] = shfl((u32)Ls[i], 6u);
+#endif
   // wrap bits: term g in lane g (g = 0..8)
   const u32 a7 = (L.tj == 0u) ? s7[0] : (L.tj == 1u ? s7[1] : s7[2]);
   const u32 a6 = (L.tj == 0u) ? s6[0] : (L.tj == 1u ? s6[1] : s6[2]);
@@ -325,7 +330,15 @@ COOP_FN void mds_arc(u32 (&s)[3], const u32 (&rc)[3], bool has_rc, const Lane &L
     const u32 qhat = umulhi32(lp, kQuotMagic) >> 25;
     const u32 q = qhat - 5u * wsum[i];
     const u64 y = Ls[i] + (u64)q * (u64)L.NP + (u64)rc[i];            // < 2^40: carries up to 2^8
+#if CUZK_COOP_MDS_LOCAL_TOP
+    // the top word of y from the two top lane values, computed by every lane itself (the constant has no words above 1):
+    // one communication round less than fetching them from lanes 7 and 6 after y is known
+    const u64 y7 = ((u64)((pk7 >> (8 * i)) & 0xffu) << 32 | (u64)l7[i]) + (u64)q * (u64)CUZK_NP7;
+    const u64 y6 = ((u64)((pk6 >> (8 * i)) & 0xffu) << 32 | (u64)l6[i]) + (u64)q * (u64)CUZK_NP6;
+    const u32 v7 = (u32)y7 + (u32)(y6 >> 32);
+#else
     const u32 v7 = top_word((u32)y, (i32)(u32)(y >> 32));
+#endif
 #if CUZK_COOP_MDS_EXACT_CARRY
     {   // v7 is the true top word unless word 6 carries out; a margin of one covers the ripple from below (coop.cuh, mds_arc)
       const u64 r6 = (u64)(u32)y + (u64)shfl((u32)(y >> 32), L.prev8);
@@ -366,9 +379,31 @@ COOP_FN void permute(u32 (&s)[3], const RcTable &rct, const Lane &L, Flags &F) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) s[i] = t[i];
   }
+#if CUZK_COOP_RC_PREFETCH
+  u32 pick0 = (L.g == 0u) ? 0xffffffffu : 0u, pick1 = (L.g == 1u) ? 0xffffffffu : 0u;   // lanes 0 and 1 hold the two words of a constant
+  coop::pin_register(pick0);
+  coop::pin_register(pick1);
+#endif
 #pragma unroll 1
   for (int round = 0; round < 64; ++round) {
     const bool full = (round < 4) || (round >= 60);
+    const bool has_rc = round < 63;
+#if CUZK_COOP_RC_PREFETCH
+    // the next round's constants: both words of each, fetched by every lane with a uniform index BEFORE the S-box and
+    // selected by lane after it, so the ~50-cycle constant loads (and no divergent branch around them) hide behind the S-box;
+    // fetched after it they were 12 % of the kernel's time (profiles/r02_tuning_notes.md)
+    u32 cw[3][2];
+    {
+      const int next = 3 * (has_rc ? round + 1 : round);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        cw[i][0] = rct(next + i, 0);
+        cw[i][1] = rct(next + i, 1);
+        coop::pin_register(cw[i][0]);
+        coop::pin_register(cw[i][1]);
+      }
+    }
+#endif
     if (full) {
       sbox<3>(s, L, F);
     } else {
@@ -377,9 +412,14 @@ COOP_FN void permute(u32 (&s)[3], const RcTable &rct, const Lane &L, Flags &F) {
       s[0] = x[0];
     }
     u32 rc[3];
-    const bool has_rc = round < 63;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) rc[i] = has_rc ? rc_word(rct, 3 * (round + 1) + i, L.g) : 0u;
+    for (int i = 0; i < 3; ++i) {
+#if CUZK_COOP_RC_PREFETCH
+      rc[i] = ((cw[i][0] & pick0) | (cw[i][1] & pick1)) & (has_rc ? 0xffffffffu : 0u);   // masks, not selects: ptxas turns the selects into branches
+#else
+      rc[i] = has_rc ? rc_word(rct, 3 * (round + 1) + i, L.g) : 0u;
+#endif
+    }
     mds_arc(s, rc, has_rc, L, F);
   }
 }
