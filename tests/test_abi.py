@@ -73,3 +73,27 @@ def test_product_does_not_reference_oracle():
                 assert "oracle_lib" not in text and "cuzk_oracle" not in text and "libcuzk_ref" not in text, f
     out = os.popen(f"ldd {cl.LIB_PATH}").read()
     assert "oracle" not in out and "cuzk_ref" not in out
+
+
+def test_library_shard_plan_equals_the_python_plan(L):
+    """cuzk_mg_shard_leaves (pure arithmetic, no GPU) deals the leaves of a sharded tree exactly like
+    distributed.plan_merkle_shards, which the gloo tests check against the single-tree oracle: contiguous, in rank order,
+    covering [0, n), cut at subtree boundaries."""
+    from cuzk_b200.distributed import plan_merkle_shards
+
+    rng = np.random.default_rng(12)
+    cases = [(1, 2, 1), (1, 8, 8), (7, 2, 3), (4096, 8, 8), (4097, 8, 8), (1 << 20, 4, 4), (1 << 26, 8, 8), (50_000, 2, 2), (9, 3, 5)]
+    cases += [(int(rng.integers(1, 1 << 22)), int(rng.integers(2, 9)), int(rng.integers(1, 9))) for _ in range(200)]
+    for n, arity, world in cases:
+        plan = plan_merkle_shards(n, arity, world)
+        at = 0
+        for rank in range(world):
+            first, count = ctypes.c_size_t(), ctypes.c_size_t()
+            L.check(L.cuzk_mg_shard_leaves(n, arity, world, rank, ctypes.byref(first), ctypes.byref(count)), "shard_leaves")
+            lo, hi = plan.rank_leaves(rank)
+            assert (first.value, count.value) == (lo, hi - lo), (n, arity, world, rank)
+            assert count.value == 0 or first.value == at, (n, arity, world, rank)
+            assert first.value % plan.span == 0 or count.value == 0
+            at += count.value
+        assert at == n, (n, arity, world)
+    assert L.cuzk_mg_shard_leaves(0, 2, 1, 0, None, None) != 0 and L.cuzk_mg_shard_leaves(5, 9, 1, 0, None, None) != 0
