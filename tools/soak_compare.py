@@ -9,6 +9,10 @@ from cuzk_b200 import api, lib as cl
 from oracle_lib import Oracle, Ref, have_ref, synth_elements
 api.initialize(0); L = cl.get_lib()
 n = 1 << (int(sys.argv[1]) if len(sys.argv) > 1 else 24)
+path = sys.argv[2] if len(sys.argv) > 2 else "default"
+if path != "default":
+    L.cuzk_debug_set_coop_max(1 << 40)
+    L.cuzk_debug_set_coop_wide_max((1 << 40) if path == "wide16" else 0)
 impl = Ref() if have_ref() else Oracle()
 threads = len(os.sched_getaffinity(0))
 before = L.cuzk_debug_fallback_count()
@@ -23,5 +27,5 @@ for start in range(0, n, step):
     got = out.cpu().numpy().view(np.uint64)
     want = impl.hash_pairs_mt(synth_elements(101, m, start), synth_elements(102, m, start), threads)
     bad += int((got != want).any(axis=1).sum())
-print(json.dumps({"pair_hashes_compared": n, "mismatches": bad, "exact_fallbacks_taken": int(L.cuzk_debug_fallback_count() - before),
+print(json.dumps({"path": path, "pair_hashes_compared": n, "mismatches": bad, "exact_fallbacks_taken": int(L.cuzk_debug_fallback_count() - before),
                   "cpu_impl": "reference" if have_ref() else "port", "cpu_threads": threads, "seconds": round(time.time() - t0, 1)}))
