@@ -45,8 +45,11 @@
 #ifndef CUZK_COOP_RC_PREFETCH
 #define CUZK_COOP_RC_PREFETCH 1   // 1: round constants are fetched before the S-box and selected after it (see permute)
 #endif
+#ifndef CUZK_COOP_PIPELINE_MDS
+#define CUZK_COOP_PIPELINE_MDS 1   // 1 (sixteen-lane file): rows 1 and 2 of a partial round's MDS layer run beside the next S-box
+#endif
 #ifndef CUZK_COOP_MDS_LOCAL_TOP
-#define CUZK_COOP_MDS_LOCAL_TOP 1   // 1: the MDS layer's top word is computed locally from lanes 7 and 6 of the sums (see mds_arc)
+#define CUZK_COOP_MDS_LOCAL_TOP 0   // 1: the MDS layer's top word is computed locally from lanes 7 and 6 of the sums (see mds_arc)
 #endif
 #ifndef CUZK_COOP_MDS_EXACT_CARRY
 #define CUZK_COOP_MDS_EXACT_CARRY 1   // 1: the carries of the MDS layer (up to 2^8 per word) are resolved exactly, see carry_exact

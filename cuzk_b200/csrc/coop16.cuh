@@ -291,74 +291,89 @@ COOP_FN u32 wrap_bit(u32 C, u32 s6, u32 s7, Flags &F) {
 
 // apply_mds_matrix (poseidon.cpp:148-167) in the linear form of mds_row_fast, followed -- when has_rc -- by the next round's
 // add_round_constants (:128-134): rc[i] is this lane's word of the constant for state element i (0 above word 1).
-COOP_FN void mds_arc(u32 (&s)[3], const u32 (&rc)[3], bool has_rc, const Lane &L, Flags &F) {
-  u64 Ls[3];
-  Ls[0] = (u64)s[0] * 7u + (u64)s[1] * 23u + (u64)s[2] * 8u;
-  Ls[1] = (u64)s[0] * 26u + (u64)s[1] * 5u + (u64)s[2] * 4u;
-  Ls[2] = (u64)s[0] * 15u + (u64)s[1] * 20u + (u64)s[2] * 9u;
-  u32 s7[3], s6[3], l7[3];
+struct MdsShared {   // what the three rows of one MDS layer share
+  u64 Ls[3];          // this lane's word of sum_j C_ij s_j, with its carry part
+  u32 l7[3], pk7, pk6;   // the same for lanes 7 and 6 (carry parts packed)
+#if CUZK_COOP_MDS_LOCAL_TOP
+  u32 l6[3];
+#endif
+  u32 wsum[3];        // wrap counts of the rows
+};
+COOP_FN void mds_prepare(MdsShared &M, const u32 (&s)[3], const Lane &L, Flags &F) {
+  M.Ls[0] = (u64)s[0] * 7u + (u64)s[1] * 23u + (u64)s[2] * 8u;
+  M.Ls[1] = (u64)s[0] * 26u + (u64)s[1] * 5u + (u64)s[2] * 4u;
+  M.Ls[2] = (u64)s[0] * 15u + (u64)s[1] * 20u + (u64)s[2] * 9u;
+  u32 s7[3], s6[3];
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     s7[j] = shfl(s[j], 7u);
     s6[j] = shfl(s[j], 6u);
   }
-  const u32 pk = (u32)(Ls[0] >> 32) | ((u32)(Ls[1] >> 32) << 8) | ((u32)(Ls[2] >> 32) << 16);   // each high part <= 46
-  const u32 pk7 = shfl(pk, 7u), pk6 = shfl(pk, 6u);
+  const u32 pk = (u32)(M.Ls[0] >> 32) | ((u32)(M.Ls[1] >> 32) << 8) | ((u32)(M.Ls[2] >> 32) << 16);   // each high part <= 46
+  M.pk7 = shfl(pk, 7u);
+  M.pk6 = shfl(pk, 6u);
 #pragma unroll
-  for (int i = 0; i < 3; ++i) l7[i] = shfl((u32)Ls[i], 7u);
+  for (int i = 0; i < 3; ++i) M.l7[i] = shfl((u32)M.Ls[i], 7u);
 #if CUZK_COOP_MDS_LOCAL_TOP
-  u32 l6[3];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) l6[i] = shfl((u32)Ls[i], 6u);
+  for (int i = 0; i < 3; ++i) M.l6[i] = shfl((u32)M.Ls[i], 6u);
 #endif
   // wrap bits: term g in lane g (g = 0..8)
   const u32 a7 = (L.tj == 0u) ? s7[0] : (L.tj == 1u ? s7[1] : s7[2]);
   const u32 a6 = (L.tj == 0u) ? s6[0] : (L.tj == 1u ? s6[1] : s6[2]);
   const u32 wb = wrap_bit(L.tc, a6, a7, F);
   const u32 bal = ballot16(wb != 0u);
-  u32 wsum[3];
-  wsum[0] = popc32(bal & 0x007u);
-  wsum[1] = popc32(bal & 0x038u);
-  wsum[2] = popc32(bal & 0x1C0u);
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    // quotient estimate from the top of S = sum_j C_ij s_j and the wrap count (mds_row_fast)
-    const u32 S7 = l7[i] + ((pk6 >> (8 * i)) & 0xffu);
-    const u32 S8 = ((pk7 >> (8 * i)) & 0xffu) + (S7 < l7[i] ? 1u : 0u);
-    const u32 a4 = (S8 << 28) | (S7 >> 4);
-    const u32 lp = a4 - ((wsum[i] * (CUZK_K7 + 1u) + 15u) >> 4);
-    const u32 qhat = umulhi32(lp, kQuotMagic) >> 25;
-    const u32 q = qhat - 5u * wsum[i];
-    const u64 y = Ls[i] + (u64)q * (u64)L.NP + (u64)rc[i];            // < 2^40: carries up to 2^8
+  M.wsum[0] = popc32(bal & 0x007u);
+  M.wsum[1] = popc32(bal & 0x038u);
+  M.wsum[2] = popc32(bal & 0x1C0u);
+}
+// row i of the layer (+ the next round's constant word rc when has_rc): this lane's word of the new state element i
+template <int i>
+COOP_FN u32 mds_row(const MdsShared &M, u32 rc, bool has_rc, const Lane &L, Flags &F) {
+  // quotient estimate from the top of S = sum_j C_ij s_j and the wrap count (mds_row_fast)
+  const u32 S7 = M.l7[i] + ((M.pk6 >> (8 * i)) & 0xffu);
+  const u32 S8 = ((M.pk7 >> (8 * i)) & 0xffu) + (S7 < M.l7[i] ? 1u : 0u);
+  const u32 a4 = (S8 << 28) | (S7 >> 4);
+  const u32 lp = a4 - ((M.wsum[i] * (CUZK_K7 + 1u) + 15u) >> 4);
+  const u32 qhat = umulhi32(lp, kQuotMagic) >> 25;
+  const u32 q = qhat - 5u * M.wsum[i];
+  const u64 y = M.Ls[i] + (u64)q * (u64)L.NP + (u64)rc;            // < 2^40: carries up to 2^8
 #if CUZK_COOP_MDS_LOCAL_TOP
-    // the top word of y from the two top lane values, computed by every lane itself (the constant has no words above 1):
-    // one communication round less than fetching them from lanes 7 and 6 after y is known
-    const u64 y7 = ((u64)((pk7 >> (8 * i)) & 0xffu) << 32 | (u64)l7[i]) + (u64)q * (u64)CUZK_NP7;
-    const u64 y6 = ((u64)((pk6 >> (8 * i)) & 0xffu) << 32 | (u64)l6[i]) + (u64)q * (u64)CUZK_NP6;
-    const u32 v7 = (u32)y7 + (u32)(y6 >> 32);
+  // the top word of y from the two top lane values, computed by every lane itself (the constant has no words above 1)
+  const u64 y7 = ((u64)((M.pk7 >> (8 * i)) & 0xffu) << 32 | (u64)M.l7[i]) + (u64)q * (u64)CUZK_NP7;
+  const u64 y6 = ((u64)((M.pk6 >> (8 * i)) & 0xffu) << 32 | (u64)M.l6[i]) + (u64)q * (u64)CUZK_NP6;
+  const u32 v7 = (u32)y7 + (u32)(y6 >> 32);
 #else
-    const u32 v7 = top_word((u32)y, (i32)(u32)(y >> 32));
+  const u32 v7 = top_word((u32)y, (i32)(u32)(y >> 32));
 #endif
+  u32 r;
 #if CUZK_COOP_MDS_EXACT_CARRY
-    {   // v7 is the true top word unless word 6 carries out; a margin of one covers the ripple from below (coop.cuh, mds_arc)
-      const u64 r6 = (u64)(u32)y + (u64)shfl((u32)(y >> 32), L.prev8);
-      F.ovf |= (L.g == 6u && r6 >= 0xFFFFFFFFull) ? 1u : 0u;
-    }
-    const u32 ge = (v7 > CUZK_P7) ? 1u : 0u;                           // y < 2p: one conditional subtraction, decided by the top word
-    F.near = umin32(F.near, v7 ^ CUZK_P7);
-    const u64 z = y + (u64)(ge ? L.NP : 0u);                           // y - p as y + (W - p): mod W, lane values stay non-negative
-    s[i] = carry_exact8((u32)z, (u32)(z >> 32), L);
-#else
-    (void)carry_pass8((u32)y, (i32)(u32)(y >> 32), L, F);   // flag only
-    const u32 ge = (v7 > CUZK_P7) ? 1u : 0u;                           // y < 2p: one conditional subtraction, decided by the top word
-    F.near = umin32(F.near, v7 ^ CUZK_P7);
-    const i64 z = (i64)y - (i64)(u64)(ge ? L.P : 0u);
-    s[i] = carry_pass8((u32)(u64)z, (i32)(z >> 32), L, F);
-#endif
-    // a state + constant whose top word reaches p's may need the reference's subtraction (arc_fast in poseidon.cuh):
-    // lane 7 adds 2^32 - p7 and flags the carry
-    if (has_rc) F.ovf |= (u32)(((u64)s[i] + (u64)L.arc) >> 32);
+  {   // v7 is the true top word unless word 6 carries out; a margin of one covers the ripple from below (coop.cuh, mds_arc)
+    const u64 r6 = (u64)(u32)y + (u64)shfl((u32)(y >> 32), L.prev8);
+    F.ovf |= (L.g == 6u && r6 >= 0xFFFFFFFFull) ? 1u : 0u;
   }
+  const u32 ge = (v7 > CUZK_P7) ? 1u : 0u;                           // y < 2p: one conditional subtraction, decided by the top word
+  F.near = umin32(F.near, v7 ^ CUZK_P7);
+  const u64 z = y + (u64)(ge ? L.NP : 0u);                           // y - p as y + (W - p): mod W, lane values stay non-negative
+  r = carry_exact8((u32)z, (u32)(z >> 32), L);
+#else
+  (void)carry_pass8((u32)y, (i32)(u32)(y >> 32), L, F);   // flag only
+  const u32 ge = (v7 > CUZK_P7) ? 1u : 0u;                           // y < 2p: one conditional subtraction, decided by the top word
+  F.near = umin32(F.near, v7 ^ CUZK_P7);
+  const i64 z = (i64)y - (i64)(u64)(ge ? L.P : 0u);
+  r = carry_pass8((u32)(u64)z, (i32)(z >> 32), L, F);
+#endif
+  // a state + constant whose top word reaches p's may need the reference's subtraction (arc_fast in poseidon.cuh):
+  // lane 7 adds 2^32 - p7 and flags the carry
+  if (has_rc) F.ovf |= (u32)(((u64)r + (u64)L.arc) >> 32);
+  return r;
+}
+COOP_FN void mds_arc(u32 (&s)[3], const u32 (&rc)[3], bool has_rc, const Lane &L, Flags &F) {
+  MdsShared M;
+  mds_prepare(M, s, L, F);
+  s[0] = mds_row<0>(M, rc[0], has_rc, L, F);
+  s[1] = mds_row<1>(M, rc[1], has_rc, L, F);
+  s[2] = mds_row<2>(M, rc[2], has_rc, L, F);
 }
 
 // this lane's word of round constant idx (all constants are < 2^64: words 0 and 1)
@@ -384,6 +399,11 @@ COOP_FN void permute(u32 (&s)[3], const RcTable &rct, const Lane &L, Flags &F) {
   coop::pin_register(pick0);
   coop::pin_register(pick1);
 #endif
+#if CUZK_COOP_PIPELINE_MDS
+  MdsShared P;          // the layer whose rows 1 and 2 are still to be evaluated
+  u32 prc[2] = {0u, 0u};
+  bool pending = false;
+#endif
 #pragma unroll 1
   for (int round = 0; round < 64; ++round) {
     const bool full = (round < 4) || (round >= 60);
@@ -404,6 +424,31 @@ COOP_FN void permute(u32 (&s)[3], const RcTable &rct, const Lane &L, Flags &F) {
       }
     }
 #endif
+#if CUZK_COOP_PIPELINE_MDS
+    // Partial rounds only pass s[0] through the S-box, so rows 1 and 2 of the previous layer are not needed before the next
+    // layer: they are evaluated next to the following round's S-box (same basic block, independent chains), where a lone
+    // warp has idle issue slots, instead of in front of it.
+    if (full) {
+      if (pending) {
+        s[1] = mds_row<1>(P, prc[0], true, L, F);
+        s[2] = mds_row<2>(P, prc[1], true, L, F);
+        pending = false;
+      }
+      sbox<3>(s, L, F);
+    } else if (pending) {
+      u32 x[1] = {s[0]};
+      const u32 t1 = mds_row<1>(P, prc[0], true, L, F);
+      const u32 t2 = mds_row<2>(P, prc[1], true, L, F);
+      sbox<1>(x, L, F);
+      s[0] = x[0];
+      s[1] = t1;
+      s[2] = t2;
+    } else {
+      u32 x[1] = {s[0]};
+      sbox<1>(x, L, F);
+      s[0] = x[0];
+    }
+#else
     if (full) {
       sbox<3>(s, L, F);
     } else {
@@ -411,6 +456,7 @@ COOP_FN void permute(u32 (&s)[3], const RcTable &rct, const Lane &L, Flags &F) {
       sbox<1>(x, L, F);
       s[0] = x[0];
     }
+#endif
     u32 rc[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -420,7 +466,19 @@ COOP_FN void permute(u32 (&s)[3], const RcTable &rct, const Lane &L, Flags &F) {
       rc[i] = has_rc ? rc_word(rct, 3 * (round + 1) + i, L.g) : 0u;
 #endif
     }
+#if CUZK_COOP_PIPELINE_MDS
+    if (full) {
+      mds_arc(s, rc, has_rc, L, F);
+    } else {   // partial rounds are 4..59: a constant always follows
+      mds_prepare(P, s, L, F);
+      s[0] = mds_row<0>(P, rc[0], true, L, F);
+      prc[0] = rc[1];
+      prc[1] = rc[2];
+      pending = true;
+    }
+#else
     mds_arc(s, rc, has_rc, L, F);
+#endif
   }
 }
 
