@@ -250,6 +250,7 @@ COOP_FN u32 wrap_bit(u32 C, u32 s6, u32 s7, Flags &F) {
 //   wrap_sums(...)                the MDS layer's three wrap counts from the nine wrap bits
 struct Wide16 {
   static constexpr int kLanes = 16;
+  static constexpr int kMinCtas = 0;    // launch bounds of the kernels of this layout: 0 = unspecified, registers are ptxas's own choice (measured best)
   static COOP_FN Lane make_lane() {
     Lane L = {};
     L.g = lane_in_group<16>();
@@ -302,6 +303,7 @@ struct Wide16 {
 
 struct Narrow8 {
   static constexpr int kLanes = 8;
+  static constexpr int kMinCtas = 2;    // two CTAs per SM is all 4736 units need; with that stated ptxas takes ~190 registers: 165 -> 162 us
   static COOP_FN Lane make_lane() {
     Lane L = {};
     L.g = lane_in_group<8>();

@@ -9,13 +9,16 @@
 #include "coop.cuh"
 #include "coop16.cuh"
 
+// launch bounds of the templated kernels: the CTA size and, per layout, how many CTAs per SM the register allocation must
+// allow.  Stating "2" makes ptxas take ~190 registers and no spills, which helps the eight-lane kernels (165 -> 162 us) and hurts
+// the sixteen-lane ones (86 -> 95 us: the scheduling lottery of profiles/r02_tuning_notes.md section 3 again), hence per layout.
 #ifndef CUZK_COOP_MIN_BLOCKS
-#define CUZK_COOP_MIN_BLOCKS 0   // CTAs per SM the register allocation must allow (tuning knob; 0 = leave it to ptxas)
+#define CUZK_COOP_MIN_BLOCKS 0   // > 0 overrides both layouts (tuning knob)
 #endif
 #if CUZK_COOP_MIN_BLOCKS > 0
 #define CUZK_COOP_BOUNDS __launch_bounds__(kCoopBlock, CUZK_COOP_MIN_BLOCKS)
 #else
-#define CUZK_COOP_BOUNDS __launch_bounds__(kCoopBlock)
+#define CUZK_COOP_BOUNDS __launch_bounds__(kCoopBlock, Y::kMinCtas)
 #endif
 constexpr int kCoopBlock = 128;                       // 8 (Wide16) or 16 (Narrow8) units per CTA, one warp per SM sub-partition
 using coop::Narrow8;
