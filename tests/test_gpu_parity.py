@@ -552,14 +552,26 @@ def test_builds_agree_with_oracle_whatever_the_kernel_mix(gpu, oracle, coop_max)
 
 def test_large_tree_built_in_groups_equals_oracle(gpu, oracle):
     """Trees of >= 2^17 leaves hash their lower levels as groups of subtrees on internal streams (the narrow upper levels of
-    one group hide behind the wide levels of the next): every stored level must still equal the oracle's, full and ragged."""
-    for arity, n in ((2, (1 << 17) + 12345), (4, 1 << 18), (8, 300_000)):
-        leaves = synth_u64_leaves(40 + arity, n)
-        want = oracle.merkle_build(leaves, arity)
-        t = gpu.DeviceMerkleTree(to_dev(leaves), arity=arity)
-        got = t.get_tree_levels()
-        assert len(got) == len(want) and all((g == w).all() for g, w in zip(got, want)), (arity, n)
-        t.close()
+    one group hide behind the wide levels of the next): every stored level must still equal the oracle's, full and ragged,
+    whatever the plan (cuzk_debug_set_build_plan: groups, streams, cooperative cap inside groups)."""
+    from cuzk_b200.lib import get_lib
+
+    L = get_lib()
+    nocap = (1 << 64) - 1
+    try:
+        for arity, n in ((2, (1 << 17) + 12345), (4, 1 << 18), (8, 300_000)):
+            leaves = synth_u64_leaves(40 + arity, n)
+            want = oracle.merkle_build(leaves, arity)
+            # the default plan, level by level on one stream, few / many groups, with and without cooperative kernels inside groups
+            for plan in (None, (1, 1, nocap), (4, 4, nocap), (16, 16, 0), (5, 3, 256)):
+                if plan is not None:
+                    L.cuzk_debug_set_build_plan(*plan)
+                t = gpu.DeviceMerkleTree(to_dev(leaves), arity=arity)
+                got = t.get_tree_levels()
+                assert len(got) == len(want) and all((g == w).all() for g, w in zip(got, want)), (arity, n, plan)
+                t.close()
+    finally:
+        L.cuzk_debug_set_build_plan(8, 8, 1184)   # the defaults (host_path.cuh)
 
 
 def test_update_semantics_duplicates_and_out_of_range(gpu, oracle):
