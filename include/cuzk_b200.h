@@ -261,13 +261,14 @@ int cuzk_debug_mds_layer(uint64_t *states, size_t n, int mode, void *stream);
  * over a group of lanes (csrc/coop.cuh), a fraction of the one-thread kernels' latency while the chip is not full -- larger
  * ones on the one-thread-per-unit kernels.  0 = never cooperative.  Among the cooperative launches those of at most
  * `wide` units use sixteen lanes per permutation (lowest latency), the others eight (fewer instructions per unit).
- * Both return the previous threshold.  Results are identical on every path. */
+ * Both return the previous threshold (defaults: 4736 and 2368 units, profiles/r02_latency_final.json).  Results are identical
+ * on every path. */
 size_t cuzk_debug_set_coop_max(size_t units);
 size_t cuzk_debug_set_coop_wide_max(size_t wide);
 /* Full-tree builds (cuzk_merkle_build / cuzk_tree_build of one tree of >= 2^17 leaves): the tree is cut into `groups` groups
  * of subtrees dealt round-robin over `streams` internal streams (<= 16); inside the groups only levels of at most
  * `group_coop_max` nodes take the cooperative kernels.  groups / streams < 1 leave the value unchanged; groups = 1 builds level
- * by level on the caller's stream.  Tuning and tests only. */
+ * by level on the caller's stream.  Defaults: 8 groups, 8 streams, 1184 nodes.  Tuning and tests only. */
 void cuzk_debug_set_build_plan(int groups, int streams, size_t group_coop_max);
 /* Host-buffer calls that move at most `bytes` (inputs + outputs) run their kernel directly on pinned host memory -- the
  * caller's buffers when they are pinned, pinned bounce copies otherwise -- instead of staging through device buffers
@@ -275,7 +276,8 @@ void cuzk_debug_set_build_plan(int groups, int streams, size_t group_coop_max);
 size_t cuzk_debug_set_direct_max(size_t bytes);
 
 /* how many units (hashes, nodes, proof levels, states) were evaluated a second time on the exact path because the fast
- * path met a comparison its top-word test could not decide (about 1e-6 per permutation on random data); a blocking read */
+ * path met a comparison its top-word test could not decide or a carry that would have to ripple twice (2 to 6 per million
+ * permutations on the one-thread kernels, 10 to 14 on the cooperative ones, on random data); a blocking read */
 uint64_t cuzk_debug_fallback_count(void);
 
 /* test hook (device pointers): the fast-path field operations on their own -- op 0 = reduce(a), 1 = multiply(a, b),
