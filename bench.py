@@ -31,6 +31,9 @@ IMAD_WIDE_PIPE_MODEL_PER_SM_CLK = 32.0   # 4 heavy-pipe cycles per warp IMAD.WID
 # root of the 2^26-leaf 8-ary tree over cuzk_synth_u64_leaves(seed 4): the same on 1, 2, 4 and 8 GPUs, and equal to the
 # single-GPU full build (tests/test_gpu_parity.py::test_config4_octary_2p26_sharded_equals_full_build)
 EXPECTED_ROOTS = {(26, 8): "0af40a4830624406744ebf70622802c7811231c8e2ce8c441c20c1c714f9c075"}
+# single-GPU time of the same 2^26-leaf 8-ary build (profiles/r02_bench_n1.json), the numerator of the strong-scaling efficiency
+# the N > 1 lines report next to their own time
+SINGLE_GPU_BUILD_MS = {(26, 8): 213.8}
 BYTES_PER_PAIR_HASH = 96        # 2 x 32 B in + 32 B out
 N_PAIRS = 1_000_000
 REF_PUBLISHED_PAIR_HASHES_PER_S = 2_145_027   # BASELINE.md section 1 (reference README.md:134, A100)
@@ -594,6 +597,11 @@ def main():
                                     "levels_stored": "every level of every subtree, on the GPU that owns it; top levels replicated",
                                     "proofs_from_shards": {"proofs": nproofs * world, "all_valid": proofs_ok, "prove_ms_rank0": 1e3 * (t1 - t0)},
                                     "roofline_frac": (perms / (ms * 1e-3)) * IMAD_PER_PERM / (imad_peak * world)}
+        t1 = SINGLE_GPU_BUILD_MS.get((args.merkle_log2, 8))
+        if t1:
+            merkle["octary_sharded"]["strong_scaling_efficiency"] = {
+                "value": t1 / (world * ms), "single_gpu_build_ms": t1,
+                "note": "committed single-GPU time of the same build (profiles/r02_bench_n1.json) / (n_gpus x this build_ms)"}
         if expected:
             assert root_hex == expected, f"sharded root {root_hex} != expected {expected}"
         assert proofs_ok, "a proof served from the sharded levels did not verify"
